@@ -195,6 +195,10 @@ int solo_get_observation(SoloHandle* h, float* d_obs, void* stream);
 int solo_get_state(SoloHandle* h, float* d_state, void* stream);
 int solo_set_state(SoloHandle* h, const float* d_state, void* stream);
 
+/* Pointgoal only: overwrite the goal of every env (d_goals float[N,2]) and recompute the
+ * potential (solo.py:277-279); parity tests use it to give oracle and GPU the same goal. */
+int solo_set_goals(SoloHandle* h, const float* d_goals, void* stream);
+
 /* Contact record of the last substep: per env, per foot: flag (0/1 as in
  * solo.py:310-323), has_point, normal force [N]. d_out float[N, 4, 3]. */
 int solo_get_contacts(SoloHandle* h, float* d_out, void* stream);

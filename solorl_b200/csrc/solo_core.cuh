@@ -1,0 +1,776 @@
+/*
+ * solo_core.cuh — per-lane math of the fused Solo8/Solo12 substep (sm_100a FP32 SIMT).
+ *
+ * Mapping: ONE LANE PER LEG, four lanes per environment.  Every spatial quantity of an
+ * environment is expressed in the AXES of the base link frame; the quantities of link k
+ * are taken about that link's own joint origin O_k (a point on the joint axis).  So a
+ * joint's motion subspace is S = (axis, 0), no rotation is ever applied to a 6x6
+ * inertia, and going from a link to its parent is a pure translation by r_k = O_k -
+ * O_{k-1}.  Taking moments about the joint's own origin is what keeps fp32 within 1e-5
+ * of the fp64 oracle: the joint-axis inertia D = a.A.a is a sum of positive terms
+ * instead of the difference of large m|r|^2 terms it would be about the base origin.
+ * The four legs are summed into the floating base with two xor-shuffles and the 6x6 base
+ * solve is done redundantly by the four lanes.  Contacts are solved in Delassus form A = P^T IA0^-1 P + blockdiag(L)
+ * by one thread per environment (see pgs_solve).
+ *
+ * This formulation is deliberately different from the CPU oracle (oracle/solo_oracle.c:
+ * link-COM frames, 6x6 transforms, one impulse-response pass per contact row), which is
+ * what makes the parity tests meaningful.  What is computed is the same physics as the
+ * reference's `p.stepSimulation()` (reference solo.py:265) restated in DESIGN.md.
+ *
+ * Everything here is `__host__ __device__` so that tests/emu can replay the exact lane
+ * program on the CPU in fp32 (the `-m "not gpu"` check of the kernel math); the product
+ * only ever runs it on the GPU.
+ */
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SOLO_HD __host__ __device__ __forceinline__
+#else
+#define SOLO_HD inline
+#endif
+
+namespace solo {
+
+constexpr int kMaxJL = 3;  /* joints per leg: 2 (Solo8: HFE,KFE) or 3 (Solo12: HAA,HFE,KFE) */
+constexpr int kRows = 12;  /* 4 feet x (normal, 2 friction) */
+
+/* joint axis of leg joint k: Solo12 = (x,y,y), Solo8 = (y,y) (solo12.urdf:48,91,134; solo.urdf:49,94) */
+template <int NJL>
+SOLO_HD constexpr int axis_of(int k) { return (NJL == 3 && k == 0) ? 0 : 1; }
+
+struct LegConst {
+  float jo[kMaxJL][3];  /* joint origin in the parent link frame */
+  float m[kMaxJL];      /* link mass (last link: lower leg + foot merged) */
+  float c[kMaxJL][3];   /* COM in the link frame (merged for the last link) */
+  float I[kMaxJL][6];   /* inertia about the COM: xx xy xz yy yz zz (merged for the last link) */
+  /* Bullet damps every URDF link separately, so the merged last link keeps two damping bodies */
+  float m_own, c_own[3];
+  float m_foot, c_foot[3];
+  float Idamp[6];       /* I_own + I_foot, each about its own COM */
+  float foot_ctr[3];    /* collision-sphere centre in the last link frame */
+};
+
+struct ModelConst {
+  LegConst leg[4];
+  float base_m;
+  float base_I[6];
+  float foot_r;
+  int njl;
+};
+
+struct SimConst {
+  float dt, inv_dt, gz, klin, kang, vmax, erp, slop, margin, mu;
+  int iters, cone, frame_skip, torque_hold;
+  int control;
+  float kp, kd, max_torque, q_limit, qd_limit;
+  int task, episode_length, H;
+  float initial_z;
+  int settle_min, settle_span;
+  float goal_reach, inv_pg_dt, flag_force, fall_z, stand_z;
+  int reset_mode;
+};
+
+/* ------------------------------------------------------------------ small helpers */
+SOLO_HD float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+SOLO_HD void cross3(const float* a, const float* b, float* o) {
+  float x = a[1] * b[2] - a[2] * b[1];
+  float y = a[2] * b[0] - a[0] * b[2];
+  float z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+SOLO_HD void cross3_add(const float* a, const float* b, float* o) {
+  o[0] += a[1] * b[2] - a[2] * b[1];
+  o[1] += a[2] * b[0] - a[0] * b[2];
+  o[2] += a[0] * b[1] - a[1] * b[0];
+}
+SOLO_HD float dot6(const float* a, const float* b) {
+  return (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + (a[3] * b[3] + a[4] * b[4] + a[5] * b[5]);
+}
+SOLO_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+SOLO_HD float solo_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+SOLO_HD void solo_sincos(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(x, s, c);
+#else
+  *s = sinf(x); *c = cosf(x);
+#endif
+}
+/* sym 3x3 stored xx xy xz yy yz zz times vector */
+SOLO_HD void sym3_mulv(const float* S, const float* x, float* y) {
+  y[0] = S[0] * x[0] + S[1] * x[1] + S[2] * x[2];
+  y[1] = S[1] * x[0] + S[3] * x[1] + S[4] * x[2];
+  y[2] = S[2] * x[0] + S[4] * x[1] + S[5] * x[2];
+}
+/* row-major 3x3 */
+SOLO_HD void mat3_mulv(const float* R, const float* x, float* y) {
+  float a = R[0] * x[0] + R[1] * x[1] + R[2] * x[2];
+  float b = R[3] * x[0] + R[4] * x[1] + R[5] * x[2];
+  float c = R[6] * x[0] + R[7] * x[1] + R[8] * x[2];
+  y[0] = a; y[1] = b; y[2] = c;
+}
+SOLO_HD void mat3T_mulv(const float* R, const float* x, float* y) {
+  float a = R[0] * x[0] + R[3] * x[1] + R[6] * x[2];
+  float b = R[1] * x[0] + R[4] * x[1] + R[7] * x[2];
+  float c = R[2] * x[0] + R[5] * x[1] + R[8] * x[2];
+  y[0] = a; y[1] = b; y[2] = c;
+}
+SOLO_HD void quat_to_rot(const float* q, float* R) { /* (x,y,z,w), base -> world */
+  float x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - w * z);       R[2] = 2.f * (x * z + w * y);
+  R[3] = 2.f * (x * y + w * z);       R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - w * x);
+  R[6] = 2.f * (x * z - w * y);       R[7] = 2.f * (y * z + w * x);       R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+/* Symmetric 6x6 spatial inertia in (angular, linear) block form:
+ *   f_ang = A w + H v ,  f_lin = H^T w + M v ;  A, M symmetric (6 floats), H full (9). */
+struct Sym6 {
+  float A[6], H[9], M[6];
+};
+SOLO_HD void sym6_zero(Sym6& I) {
+  for (int i = 0; i < 6; i++) { I.A[i] = 0.f; I.M[i] = 0.f; }
+  for (int i = 0; i < 9; i++) I.H[i] = 0.f;
+}
+SOLO_HD void sym6_mulv(const Sym6& I, const float* x, float* y) {
+  float a[3], b[3];
+  sym3_mulv(I.A, x, a);
+  mat3_mulv(I.H, x + 3, b);
+  y[0] = a[0] + b[0]; y[1] = a[1] + b[1]; y[2] = a[2] + b[2];
+  mat3T_mulv(I.H, x, a);
+  sym3_mulv(I.M, x + 3, b);
+  y[3] = a[0] + b[0]; y[4] = a[1] + b[1]; y[5] = a[2] + b[2];
+}
+/* I -= h h^T * s */
+SOLO_HD void sym6_rank1_sub(Sym6& I, const float* h, float s) {
+  float g[6];
+  for (int i = 0; i < 6; i++) g[i] = h[i] * s;
+  I.A[0] -= g[0] * h[0]; I.A[1] -= g[0] * h[1]; I.A[2] -= g[0] * h[2];
+  I.A[3] -= g[1] * h[1]; I.A[4] -= g[1] * h[2]; I.A[5] -= g[2] * h[2];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) I.H[3 * i + j] -= g[i] * h[3 + j];
+  I.M[0] -= g[3] * h[3]; I.M[1] -= g[3] * h[4]; I.M[2] -= g[3] * h[5];
+  I.M[3] -= g[4] * h[4]; I.M[4] -= g[4] * h[5]; I.M[5] -= g[5] * h[5];
+}
+/* I += rigid body (mass m, COM c, inertia about COM Ic in the common frame) */
+SOLO_HD void sym6_add_rigid(Sym6& I, float m, const float* c, const float* Ic) {
+  float cc = dot3(c, c);
+  float mx = m * c[0], my = m * c[1], mz = m * c[2];
+  I.A[0] += Ic[0] + m * cc - mx * c[0];
+  I.A[1] += Ic[1] - mx * c[1];
+  I.A[2] += Ic[2] - mx * c[2];
+  I.A[3] += Ic[3] + m * cc - my * c[1];
+  I.A[4] += Ic[4] - my * c[2];
+  I.A[5] += Ic[5] + m * cc - mz * c[2];
+  /* H = m [c]x */
+  I.H[1] -= mz; I.H[2] += my;
+  I.H[3] += mz; I.H[5] -= mx;
+  I.H[6] -= my; I.H[7] += mx;
+  I.M[0] += m; I.M[3] += m; I.M[5] += m;
+}
+
+/* Re-express a spatial inertia taken about O' = O + r about O (pure translation):
+ *   M stays, H <- H + [r]x M =: T,  A <- A + [r]x H^T - T [r]x   (old H on the right-hand side). */
+SOLO_HD void sym6_shift(Sym6& I, const float* r) {
+  const float M[9] = {I.M[0], I.M[1], I.M[2], I.M[1], I.M[3], I.M[4], I.M[2], I.M[4], I.M[5]};
+  float T[9];
+  /* columns of [r]x M = r x (columns of M) */
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const float mc[3] = {M[j], M[3 + j], M[6 + j]};
+    float t[3];
+    cross3(r, mc, t);
+    T[j] = I.H[j] + t[0]; T[3 + j] = I.H[3 + j] + t[1]; T[6 + j] = I.H[6 + j] + t[2];
+  }
+  /* X = [r]x H^T : column j of H^T is row j of H */
+  float X[9];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const float hr[3] = {I.H[3 * j], I.H[3 * j + 1], I.H[3 * j + 2]};
+    float t[3];
+    cross3(r, hr, t);
+    X[j] = t[0]; X[3 + j] = t[1]; X[6 + j] = t[2];
+  }
+  /* Y = T [r]x : row i of Y = (row i of T) x r  */
+  float Y[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float tr[3] = {T[3 * i], T[3 * i + 1], T[3 * i + 2]};
+    float t[3];
+    cross3(tr, r, t);
+    Y[3 * i] = t[0]; Y[3 * i + 1] = t[1]; Y[3 * i + 2] = t[2];
+  }
+  I.A[0] += X[0] - Y[0];
+  I.A[1] += 0.5f * ((X[1] - Y[1]) + (X[3] - Y[3]));
+  I.A[2] += 0.5f * ((X[2] - Y[2]) + (X[6] - Y[6]));
+  I.A[3] += X[4] - Y[4];
+  I.A[4] += 0.5f * ((X[5] - Y[5]) + (X[7] - Y[7]));
+  I.A[5] += X[8] - Y[8];
+#pragma unroll
+  for (int i = 0; i < 9; i++) I.H[i] = T[i];
+}
+
+/* LDL^T factor of the 6x6 base articulated inertia */
+struct Ldl6 {
+  float L[15];   /* strictly lower, row-major: (1,0) (2,0) (2,1) (3,0) ... (5,4) */
+  float dinv[6];
+};
+SOLO_HD int ldl_idx(int i, int j) { return i * (i - 1) / 2 + j; }
+SOLO_HD void ldl6_factor(const Sym6& I, Ldl6& F) {
+  float a[6][6];
+  a[0][0] = I.A[0]; a[1][0] = I.A[1]; a[2][0] = I.A[2]; a[1][1] = I.A[3]; a[2][1] = I.A[4]; a[2][2] = I.A[5];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) a[3 + i][j] = I.H[3 * j + i]; /* lower-left block = H^T */
+  a[3][3] = I.M[0]; a[4][3] = I.M[1]; a[5][3] = I.M[2]; a[4][4] = I.M[3]; a[5][4] = I.M[4]; a[5][5] = I.M[5];
+  float d[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    float s = a[j][j];
+#pragma unroll
+    for (int k = 0; k < j; k++) s -= F.L[ldl_idx(j, k)] * F.L[ldl_idx(j, k)] * d[k];
+    d[j] = s;
+    F.dinv[j] = 1.0f / s;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      float t = a[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) t -= F.L[ldl_idx(i, k)] * F.L[ldl_idx(j, k)] * d[k];
+      F.L[ldl_idx(i, j)] = t * F.dinv[j];
+    }
+  }
+}
+SOLO_HD void ldl6_solve(const Ldl6& F, float* x) { /* in place */
+#pragma unroll
+  for (int i = 1; i < 6; i++) {
+#pragma unroll
+    for (int k = 0; k < i; k++) x[i] -= F.L[ldl_idx(i, k)] * x[k];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) x[i] *= F.dinv[i];
+#pragma unroll
+  for (int i = 4; i >= 0; i--) {
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) x[i] -= F.L[ldl_idx(k, i)] * x[k];
+  }
+}
+
+/* ------------------------------------------------------------------ state */
+struct BaseState {        /* world frame; replicated in the four lanes of an env */
+  float p[3], q[4], v[3], w[3];
+};
+struct BaseWork {
+  float R[9];             /* base -> world */
+  float wb[3], vb[3];     /* base velocity in base coordinates */
+  Ldl6 F;                 /* factor of the base articulated inertia */
+};
+template <int NJL>
+struct Lane {             /* one leg */
+  float q[NJL], qd[NJL];
+  float ax[NJL][3];       /* joint axis in base axes */
+  float r[NJL][3];        /* O_k - O_{k-1} in base axes (O_{-1} = base origin) */
+  float cJ[NJL][6], h[NJL][6], invD[NJL], u[NJL];
+  float Rl[9], ol[3];     /* rotation of the last link, and O_last relative to the base origin */
+  /* contact */
+  float sP[NJL][3];       /* S_k . (wrench of unit impulse m propagated to joint k) */
+  float P[3][6], K[3][6]; /* base wrench per unit impulse, IA0^-1 P */
+  float Lm[6];            /* leg-local 3x3 block (sym): sum_k sP sP^T invD */
+  float b[3];             /* target relative velocity (rhs before scaling) */
+  float dist;
+  int active;
+};
+
+SOLO_HD void base_prepare(const BaseState& s, BaseWork& w) {
+  quat_to_rot(s.q, w.R);
+  mat3T_mulv(w.R, s.w, w.wb);
+  mat3T_mulv(w.R, s.v, w.vb);
+}
+
+/* Passes 1+2 of the articulated-body algorithm for one leg (outward kinematics and bias
+ * forces, then inward articulated inertia).  Result: the leg's articulated inertia and
+ * bias force as seen by the base (IAleg, pAleg), about the base origin, base axes. */
+template <int NJL>
+SOLO_HD void leg_inward(const LegConst& lc, const SimConst& sc, const BaseWork& bw, Lane<NJL>& ln,
+                        const float* tau, Sym6& IAleg, float* pAleg) {
+  float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  float o[3] = {0.f, 0.f, 0.f};
+  float va[3] = {bw.wb[0], bw.wb[1], bw.wb[2]};
+  float vl[3] = {bw.vb[0], bw.vb[1], bw.vb[2]};   /* linear velocity of the point at O_k */
+  float pk[NJL][6], com[NJL][3], Ic[NJL][6];
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    float t[3];
+    float* r = ln.r[k];
+    mat3_mulv(R, lc.jo[k], r);
+    o[0] += r[0]; o[1] += r[1]; o[2] += r[2];
+    cross3_add(va, r, vl);                           /* move the reference point to O_k */
+    constexpr int kAxX = 0;
+    const int ax = axis_of<NJL>(k);
+    float* a = ln.ax[k];
+    a[0] = R[ax]; a[1] = R[3 + ax]; a[2] = R[6 + ax];
+    float sn, cs;
+    solo_sincos(ln.q[k], &sn, &cs);
+    if (ax == kAxX) { /* R <- R Rx(q): col1' = c col1 + s col2 ; col2' = -s col1 + c col2 */
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float c1 = R[3 * i + 1], c2 = R[3 * i + 2];
+        R[3 * i + 1] = cs * c1 + sn * c2;
+        R[3 * i + 2] = cs * c2 - sn * c1;
+      }
+    } else {          /* R <- R Ry(q): col0' = c col0 - s col2 ; col2' = s col0 + c col2 */
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float c0 = R[3 * i + 0], c2 = R[3 * i + 2];
+        R[3 * i + 0] = cs * c0 - sn * c2;
+        R[3 * i + 2] = sn * c0 + cs * c2;
+      }
+    }
+    /* joint velocity (a qd, 0) and velocity-product acceleration cJ = v x (a qd, 0) */
+    float qd = ln.qd[k];
+    float wJ[3] = {a[0] * qd, a[1] * qd, a[2] * qd};
+    cross3(va, wJ, ln.cJ[k]);
+    cross3(vl, wJ, ln.cJ[k] + 3);
+    va[0] += wJ[0]; va[1] += wJ[1]; va[2] += wJ[2];
+    /* COM (relative to O_k) and rotated inertia */
+    mat3_mulv(R, lc.c[k], com[k]);
+    {
+      const float* I = lc.I[k];
+      float T[9];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        T[3 * i + 0] = R[3 * i] * I[0] + R[3 * i + 1] * I[1] + R[3 * i + 2] * I[2];
+        T[3 * i + 1] = R[3 * i] * I[1] + R[3 * i + 1] * I[3] + R[3 * i + 2] * I[4];
+        T[3 * i + 2] = R[3 * i] * I[2] + R[3 * i + 1] * I[4] + R[3 * i + 2] * I[5];
+      }
+      Ic[k][0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2];
+      Ic[k][1] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5];
+      Ic[k][2] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8];
+      Ic[k][3] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5];
+      Ic[k][4] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8];
+      Ic[k][5] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8];
+    }
+    /* momentum and velocity-product bias  p = v x* (I v), moments about O_k */
+    float vc[3], l[3], nc[3], nO[3];
+    cross3(va, com[k], vc);
+    vc[0] += vl[0]; vc[1] += vl[1]; vc[2] += vl[2];
+    float m = lc.m[k];
+    l[0] = m * vc[0]; l[1] = m * vc[1]; l[2] = m * vc[2];
+    sym3_mulv(Ic[k], va, nc);
+    cross3(com[k], l, nO);
+    nO[0] += nc[0]; nO[1] += nc[1]; nO[2] += nc[2];
+    cross3(va, nO, pk[k]);
+    cross3_add(vl, l, pk[k]);
+    cross3(va, l, pk[k] + 3);
+    /* Bullet link damping: drag  m v_c (k + k|v_c|)  and  I w (k + k|w|)  per URDF link */
+    float wn = sqrtf(dot3(va, va));
+    float sa = sc.kang + sc.kang * wn;
+    if (k < NJL - 1) {
+      float sl = sc.klin + sc.klin * sqrtf(dot3(vc, vc));
+      float f[3] = {l[0] * sl, l[1] * sl, l[2] * sl};
+      pk[k][3] += f[0]; pk[k][4] += f[1]; pk[k][5] += f[2];
+      cross3_add(com[k], f, pk[k]);
+      pk[k][0] += nc[0] * sa; pk[k][1] += nc[1] * sa; pk[k][2] += nc[2] * sa;
+    } else {
+      float cb[3], vb2[3], f[3];
+      /* lower leg proper */
+      mat3_mulv(R, lc.c_own, cb);
+      cross3(va, cb, vb2);
+      vb2[0] += vl[0]; vb2[1] += vl[1]; vb2[2] += vl[2];
+      float sl = lc.m_own * (sc.klin + sc.klin * sqrtf(dot3(vb2, vb2)));
+      f[0] = vb2[0] * sl; f[1] = vb2[1] * sl; f[2] = vb2[2] * sl;
+      pk[k][3] += f[0]; pk[k][4] += f[1]; pk[k][5] += f[2];
+      cross3_add(cb, f, pk[k]);
+      /* foot */
+      mat3_mulv(R, lc.c_foot, cb);
+      cross3(va, cb, vb2);
+      vb2[0] += vl[0]; vb2[1] += vl[1]; vb2[2] += vl[2];
+      sl = lc.m_foot * (sc.klin + sc.klin * sqrtf(dot3(vb2, vb2)));
+      f[0] = vb2[0] * sl; f[1] = vb2[1] * sl; f[2] = vb2[2] * sl;
+      pk[k][3] += f[0]; pk[k][4] += f[1]; pk[k][5] += f[2];
+      cross3_add(cb, f, pk[k]);
+      /* angular: R Idamp R^T w */
+      float wl[3], Iw[3], tw[3];
+      mat3T_mulv(R, va, wl);
+      sym3_mulv(lc.Idamp, wl, Iw);
+      mat3_mulv(R, Iw, tw);
+      pk[k][0] += tw[0] * sa; pk[k][1] += tw[1] * sa; pk[k][2] += tw[2] * sa;
+    }
+    (void)t;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) ln.Rl[i] = R[i];
+  ln.ol[0] = o[0]; ln.ol[1] = o[1]; ln.ol[2] = o[2];
+
+  /* inward pass: carry the articulated inertia up the chain, translating it from O_k to
+   * O_{k-1} after each joint */
+  sym6_zero(IAleg);
+#pragma unroll
+  for (int i = 0; i < 6; i++) pAleg[i] = 0.f;
+#pragma unroll
+  for (int k = NJL - 1; k >= 0; k--) {
+    sym6_add_rigid(IAleg, lc.m[k], com[k], Ic[k]);
+#pragma unroll
+    for (int i = 0; i < 6; i++) pAleg[i] += pk[k][i];
+    const float* a = ln.ax[k];
+    float* h = ln.h[k];
+    sym3_mulv(IAleg.A, a, h);          /* h = IA (a, 0) */
+    mat3T_mulv(IAleg.H, a, h + 3);
+    float D = dot3(a, h);
+    float invD = 1.0f / D;
+    ln.invD[k] = invD;
+    float u = tau[k] - dot3(a, pAleg);
+    ln.u[k] = u;
+    sym6_rank1_sub(IAleg, h, invD);
+    float Ic6[6];
+    sym6_mulv(IAleg, ln.cJ[k], Ic6);
+    float ud = u * invD;
+#pragma unroll
+    for (int i = 0; i < 6; i++) pAleg[i] += Ic6[i] + h[i] * ud;
+    /* translate to the parent's origin */
+    sym6_shift(IAleg, ln.r[k]);
+    cross3_add(ln.r[k], pAleg + 3, pAleg);
+  }
+}
+
+/* Base rigid body: add to the summed leg inertias / bias, factor, solve a0 = -IA0^-1 pA0. */
+SOLO_HD void base_solve(const ModelConst& mc, const SimConst& sc, BaseWork& bw, Sym6& IA0,
+                        float* pA0, float* a0) {
+  const float zero3[3] = {0.f, 0.f, 0.f};
+  sym6_add_rigid(IA0, mc.base_m, zero3, mc.base_I);
+  float nb[3], l[3];
+  sym3_mulv(mc.base_I, bw.wb, nb);
+  l[0] = mc.base_m * bw.vb[0]; l[1] = mc.base_m * bw.vb[1]; l[2] = mc.base_m * bw.vb[2];
+  float sa = sc.kang + sc.kang * sqrtf(dot3(bw.wb, bw.wb));
+  float sl = sc.klin + sc.klin * sqrtf(dot3(bw.vb, bw.vb));
+  float pb[6];
+  cross3(bw.wb, nb, pb);
+  cross3(bw.wb, l, pb + 3);
+  pb[0] += nb[0] * sa; pb[1] += nb[1] * sa; pb[2] += nb[2] * sa;
+  pb[3] += l[0] * sl; pb[4] += l[1] * sl; pb[5] += l[2] * sl;
+#pragma unroll
+  for (int i = 0; i < 6; i++) pA0[i] += pb[i];
+  ldl6_factor(IA0, bw.F);
+#pragma unroll
+  for (int i = 0; i < 6; i++) a0[i] = -pA0[i];
+  ldl6_solve(bw.F, a0);
+}
+
+/* Pass 3: joint accelerations of one leg from the base spatial acceleration. */
+template <int NJL>
+SOLO_HD void leg_outward(const Lane<NJL>& ln, const float* a0, float* qdd) {
+  float a[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) a[i] = a0[i];
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    cross3_add(a, ln.r[k], a + 3);                   /* reference point -> O_k */
+#pragma unroll
+    for (int i = 0; i < 6; i++) a[i] += ln.cJ[k][i];
+    float qa = (ln.u[k] - dot6(ln.h[k], a)) * ln.invD[k];
+    qdd[k] = qa;
+    a[0] += ln.ax[k][0] * qa; a[1] += ln.ax[k][1] * qa; a[2] += ln.ax[k][2] * qa;
+  }
+}
+
+/* World-frame base acceleration from the spatial one: gravity enters here (uniform field:
+ * it does not change relative accelerations), and w x v converts the derivative of
+ * body-frame velocity coordinates into the classical acceleration of the base origin. */
+SOLO_HD void base_world_acc(const SimConst& sc, const BaseWork& bw, const float* a0,
+                            float* angacc_w, float* linacc_w) {
+  float al[3];
+  cross3(bw.wb, bw.vb, al);
+  /* gravity in base coordinates = gz * (third row of R) */
+  al[0] += a0[3] + sc.gz * bw.R[6];
+  al[1] += a0[4] + sc.gz * bw.R[7];
+  al[2] += a0[5] + sc.gz * bw.R[8];
+  mat3_mulv(bw.R, a0, angacc_w);
+  mat3_mulv(bw.R, al, linacc_w);
+}
+
+SOLO_HD void base_add_velocity(const SimConst& sc, BaseState& s, const float* dw, const float* dv,
+                               float scale) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    s.w[i] = clampf(s.w[i] + scale * dw[i], -sc.vmax, sc.vmax);
+    s.v[i] = clampf(s.v[i] + scale * dv[i], -sc.vmax, sc.vmax);
+  }
+}
+
+/* Contact rows of one foot.  bw must hold the PRE-update rotation (poses do not change
+ * between the ABA and the constraint solve) and st the POST-update velocity v*. */
+template <int NJL>
+SOLO_HD void contact_setup(const LegConst& lc, const ModelConst& mc, const SimConst& sc,
+                           const BaseState& st, const BaseWork& bw, Lane<NJL>& ln) {
+  float rfl[3];                                             /* sphere centre relative to O_last */
+  mat3_mulv(ln.Rl, lc.foot_ctr, rfl);
+  const float nb[3] = {bw.R[6], bw.R[7], bw.R[8]};          /* world z in base coordinates */
+  float rf[3] = {ln.ol[0] + rfl[0], ln.ol[1] + rfl[1], ln.ol[2] + rfl[2]};
+  float height = st.p[2] + dot3(nb, rf);
+  ln.dist = height - mc.foot_r;
+  ln.active = ln.dist < sc.margin;
+  float rc[3] = {rfl[0] - mc.foot_r * nb[0], rfl[1] - mc.foot_r * nb[1], rfl[2] - mc.foot_r * nb[2]};
+  /* btPlaneSpace1((0,0,1)) = (0,-1,0), (1,0,0), expressed in base coordinates */
+  float d[3][3] = {{nb[0], nb[1], nb[2]}, {-bw.R[3], -bw.R[4], -bw.R[5]}, {bw.R[0], bw.R[1], bw.R[2]}};
+  /* spatial velocity of the last link about O_last with the updated velocities */
+  float v6[6];
+  mat3T_mulv(bw.R, st.w, v6);
+  mat3T_mulv(bw.R, st.v, v6 + 3);
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    cross3_add(v6, ln.r[k], v6 + 3);
+    v6[0] += ln.ax[k][0] * ln.qd[k]; v6[1] += ln.ax[k][1] * ln.qd[k]; v6[2] += ln.ax[k][2] * ln.qd[k];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) ln.Lm[i] = 0.f;
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    float w[6];
+    cross3(rc, d[m], w);
+    w[3] = d[m][0]; w[4] = d[m][1]; w[5] = d[m][2];
+    float vel = dot6(w, v6);
+#pragma unroll
+    for (int k = NJL - 1; k >= 0; k--) {
+      float s = dot3(ln.ax[k], w);
+      ln.sP[k][m] = s;
+      float g = s * ln.invD[k];
+#pragma unroll
+      for (int i = 0; i < 6; i++) w[i] -= ln.h[k][i] * g;
+      cross3_add(ln.r[k], w + 3, w);                        /* moments about the parent's origin */
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) { ln.P[m][i] = w[i]; ln.K[m][i] = w[i]; }
+    ldl6_solve(bw.F, ln.K[m]);
+    if (m == 0) {
+      float pen = ln.dist + sc.slop;
+      /* speculative contact while separated, ERP push-out while penetrating */
+      ln.b[0] = -vel - pen * (pen > 0.f ? sc.inv_dt : sc.erp * sc.inv_dt);
+    } else {
+      ln.b[m] = -vel;
+    }
+  }
+  /* leg-local block L = sum_k sP_k sP_k^T invD_k  (xx xy xz yy yz zz over m,n) */
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    float g0 = ln.sP[k][0] * ln.invD[k], g1 = ln.sP[k][1] * ln.invD[k], g2 = ln.sP[k][2] * ln.invD[k];
+    ln.Lm[0] += g0 * ln.sP[k][0]; ln.Lm[1] += g0 * ln.sP[k][1]; ln.Lm[2] += g0 * ln.sP[k][2];
+    ln.Lm[3] += g1 * ln.sP[k][1]; ln.Lm[4] += g1 * ln.sP[k][2]; ln.Lm[5] += g2 * ln.sP[k][2];
+  }
+}
+
+/* Global row index of (foot i, direction m): normals first, then friction pairs
+ * (the order btMultiBodyConstraintSolver sweeps them). */
+SOLO_HD constexpr int row_of(int foot, int m) { return m == 0 ? foot : 4 + 2 * foot + (m - 1); }
+
+/* Rows of the scaled Delassus matrix owned by one foot, built one column block at a time:
+ *   A = P^T IA0^-1 P + blockdiag(L),  B[r][c] = A[r][c] / A[r][r],  g0[r] = b[r] / A[r][r].
+ * assemble_block adds the 3x3 block against foot j (Kj = K of foot j, fetched from that
+ * lane); assemble_finish adds the leg-local block, scales and stores.  Inactive feet
+ * produce zero rows/columns.  Stored at Bout[(r*kRows + c)*stride], g0out[r*stride]. */
+template <int NJL>
+SOLO_HD void assemble_block(const Lane<NJL>& ln, int j, const float Kj[3][6], float rows[3][kRows]) {
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+#pragma unroll
+    for (int n = 0; n < 3; n++) rows[m][row_of(j, n)] = dot6(ln.P[m], Kj[n]);
+  }
+}
+template <int NJL>
+SOLO_HD void assemble_finish(const Lane<NJL>& ln, int foot, float rows[3][kRows],
+                             unsigned active_mask, float* Bout, float* g0out, int stride) {
+  const int lidx[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const int r = row_of(foot, m);
+#pragma unroll
+    for (int n = 0; n < 3; n++) rows[m][row_of(foot, n)] += ln.Lm[lidx[m][n]];
+    float invd = ln.active ? 1.0f / rows[m][r] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+#pragma unroll
+      for (int n = 0; n < 3; n++) {
+        const int c = row_of(j, n);
+        float v = (((active_mask >> j) & 1u) && c != r) ? rows[m][c] * invd : 0.f;
+        Bout[(r * kRows + c) * stride] = v;
+      }
+    }
+    g0out[r * stride] = ln.b[m] * invd;
+  }
+}
+
+/* Projected Gauss-Seidel on the scaled Delassus system, one thread per environment.
+ * State g[r] = lambda[r] + (rhs[r] - sum_c A[r][c] lambda[c]) / A[r][r] is the value row r
+ * would take if relaxed now, so relaxing a row is clamp + 11 independent FMAs.
+ * Sweep order and projections restate btMultiBodyConstraintSolver::solveSingleIteration:
+ * all normal rows (lambda >= 0), then per contact the friction pair, both candidates taken
+ * from the same state and projected radially onto the circle of radius mu*lambda_n
+ * (resolveConeFrictionConstraintRows; atan2/sin/cos there == x/|x| scaling here), or row by
+ * row onto [-mu lambda_n, mu lambda_n] when cone friction is off.  No warm start, fixed
+ * iteration count. */
+SOLO_HD void pgs_solve(const float* B, const float* g0, int stride, int iters, int cone, float mu,
+                       unsigned feet_mask, float* lam_out) {
+  float Bm[kRows][kRows], g[kRows], lam[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; r++) {
+    g[r] = g0[r * stride];
+    lam[r] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kRows; c++) Bm[r][c] = B[(r * kRows + c) * stride];
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      if (!(feet_mask & (1u << f))) continue;
+      float nv = fmaxf(g[f], 0.f);
+      float d = nv - lam[f];
+      lam[f] = nv;
+#pragma unroll
+      for (int s = 0; s < kRows; s++)
+        if (s != f) g[s] -= Bm[s][f] * d;
+    }
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      if (!(feet_mask & (1u << f))) continue;
+      const int a = 4 + 2 * f, b = 5 + 2 * f;
+      float lim = mu * lam[f];
+      if (cone) {
+        float sA = g[a], sB = g[b];
+        float n2 = sA * sA + sB * sB;
+        float inv = n2 > 0.f ? solo_rsqrt(n2) : 0.f;
+        float limA = lim * fabsf(sA) * inv;
+        float limB = n2 > 0.f ? lim * fabsf(sB) * inv : lim;
+        float nA = clampf(sA, -limA, limA), nB = clampf(sB, -limB, limB);
+        float dA = nA - lam[a], dB = nB - lam[b];
+        lam[a] = nA; lam[b] = nB;
+#pragma unroll
+        for (int s = 0; s < kRows; s++) {
+          if (s == a) g[s] -= Bm[s][b] * dB;
+          else if (s == b) g[s] -= Bm[s][a] * dA;
+          else g[s] -= Bm[s][a] * dA + Bm[s][b] * dB;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int r = q ? b : a;
+          float nv = clampf(g[r], -lim, lim);
+          float d = nv - lam[r];
+          lam[r] = nv;
+#pragma unroll
+          for (int s = 0; s < kRows; s++)
+            if (s != r) g[s] -= Bm[s][r] * d;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kRows; r++) lam_out[r * stride] = lam[r];
+}
+
+/* Wrench on the base produced by this foot's impulses, already multiplied by IA0^-1:
+ * dv0_part = K lambda (sum over feet = base velocity change, base coordinates). */
+template <int NJL>
+SOLO_HD void impulse_base_part(const Lane<NJL>& ln, const float* lam3, float* dv0_part) {
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+    dv0_part[i] = ln.K[0][i] * lam3[0] + ln.K[1][i] * lam3[1] + ln.K[2][i] * lam3[2];
+}
+
+/* Joint velocity change of one leg for its own impulses and the base velocity change. */
+template <int NJL>
+SOLO_HD void impulse_leg(Lane<NJL>& ln, const SimConst& sc, const float* lam3, const float* dv0) {
+  float a[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) a[i] = dv0[i];
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    cross3_add(a, ln.r[k], a + 3);
+    float us = ln.sP[k][0] * lam3[0] + ln.sP[k][1] * lam3[1] + ln.sP[k][2] * lam3[2];
+    float dq = (us - dot6(ln.h[k], a)) * ln.invD[k];
+    a[0] += ln.ax[k][0] * dq; a[1] += ln.ax[k][1] * dq; a[2] += ln.ax[k][2] * dq;
+    ln.qd[k] = clampf(ln.qd[k] + dq, -sc.vmax, sc.vmax);
+  }
+}
+
+/* Semi-implicit Euler position update ([3P] btMultiBody::stepPositionsMultiDof). */
+SOLO_HD void integrate_base(const SimConst& sc, BaseState& s) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) s.p[i] += sc.dt * s.v[i];
+  float wn = sqrtf(dot3(s.w, s.w));
+  float ha = 0.5f * wn * sc.dt;
+  float sn, cs;
+  solo_sincos(ha, &sn, &cs);
+  float k = wn > 1e-12f ? sn / wn : 0.5f * sc.dt;
+  float dx = s.w[0] * k, dy = s.w[1] * k, dz = s.w[2] * k, dw = cs;
+  float x = s.q[0], y = s.q[1], z = s.q[2], w = s.q[3];
+  float nx = dw * x + dx * w + dy * z - dz * y;
+  float ny = dw * y - dx * z + dy * w + dz * x;
+  float nz = dw * z + dx * y - dy * x + dz * w;
+  float nw = dw * w - dx * x - dy * y - dz * z;
+  float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+  s.q[0] = nx * inv; s.q[1] = ny * inv; s.q[2] = nz * inv; s.q[3] = nw * inv;
+}
+
+/* ------------------------------------------------------------------ env arithmetic */
+/* [3P] p.getEulerFromQuaternion = btQuaternion::getEulerZYX -> roll, pitch, yaw */
+SOLO_HD void quat_to_euler(const float* q, float* rpy) {
+  const float kHalfPi = 1.57079632679489661923f;
+  float x = q[0], y = q[1], z = q[2], w = q[3];
+  float sqx = x * x, sqy = y * y, sqz = z * z, sqw = w * w;
+  float sarg = -2.f * (x * z - w * y);
+  if (sarg <= -0.99999f) {
+    rpy[1] = -kHalfPi; rpy[0] = 0.f; rpy[2] = 2.f * atan2f(x, -y);
+  } else if (sarg >= 0.99999f) {
+    rpy[1] = kHalfPi; rpy[0] = 0.f; rpy[2] = 2.f * atan2f(-x, y);
+  } else {
+    rpy[1] = asinf(sarg);
+    rpy[0] = atan2f(2.f * (y * z + w * x), sqw - sqx - sqy + sqz);
+    rpy[2] = atan2f(2.f * (x * y + w * z), sqw + sqx - sqy - sqz);
+  }
+}
+/* solo.py:206: (e % 2*pi) / (2*pi) == ((e mod 2) * pi) / (2 pi) with Python's floor-mod */
+SOLO_HD float euler_obs(float e) {
+  float r = fmodf(e, 2.0f);
+  if (r < 0.f) r += 2.0f;
+  return r * 0.5f;
+}
+/* solo.py:224-259 + controllers/PD.py:3-10 for one joint */
+SOLO_HD float action_to_torque(const SimConst& sc, float a, float q, float qd, float kp, float kd) {
+  float ac = clampf(a, -1.f, 1.f);
+  if (sc.control == 0) return ac * sc.max_torque;
+  float t = kp * (ac * sc.q_limit - q) - kd * qd;
+  return clampf(t, -sc.max_torque, sc.max_torque);
+}
+
+/* Philox4x32-10, counter = (env id lo, env id hi, episode, draw), key = seed */
+SOLO_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+SOLO_HD void philox4x32_10(uint32_t* c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0 = mulhi32(0xD2511F53u, c[0]), l0 = 0xD2511F53u * c[0];
+    uint32_t h1 = mulhi32(0xCD9E8D57u, c[2]), l1 = 0xCD9E8D57u * c[2];
+    uint32_t n0 = h1 ^ c[1] ^ k0, n2 = h0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = l1; c[2] = n2; c[3] = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+SOLO_HD float u01(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
+/* solo.py:325-330 */
+SOLO_HD void sample_goal(const uint32_t* w, float goal_radius, float* g) {
+  float gx = 1.0f + (goal_radius - 1.0f) * u01(w[1]);
+  float gy = 1.0f + (goal_radius - 1.0f) * u01(w[2]);
+  g[0] = (w[3] & 1u) ? gx : -gx;
+  g[1] = (w[3] & 2u) ? gy : -gy;
+}
+
+}  // namespace solo

@@ -1,0 +1,1040 @@
+/*
+ * solo_kernels.cu — sm_100a kernels and the C-ABI (include/solo_b200.h) of the batched
+ * Solo8/Solo12 env step.
+ *
+ * step_kernel: ONE launch per env step.  A block owns 32 environments:
+ *   warps 0-3  "leg lanes": thread t = (env t/4, leg t%4); articulated-body dynamics,
+ *              contact-row assembly, impulse application, integration, observation /
+ *              reward / termination / auto-reset.  Cross-leg sums are xor-shuffles.
+ *   warp  4    "solver lanes": thread = one env; fixed-iteration projected Gauss-Seidel on
+ *              the 12x12 scaled Delassus system handed over through shared memory.
+ * While one role works the other waits at a block barrier, so idle *warps* (free) replace
+ * idle *lanes* (which would cost issue slots): the sequential PGS sweep runs with all 32
+ * lanes busy instead of 1 in 4.
+ *
+ * HBM layout (structure of arrays, fp32):
+ *   base  [cap][16]  : pos3 quat4 linvel3 angvel3 goal2 potential1   (4 x float4 per env)
+ *   q,qd  [NJL][cap][4] : joint k of leg l of env e at ((k*cap+e)*4+l)  (one float4 per env and k,
+ *                      consecutive threads read consecutive words)
+ *   cforce[cap][4]   : normal force of the last substep per foot, <0 = no contact point
+ *   hist  [H][cap][D0], book [cap] (EnvBook), stats [cap] (SoloEpisodeStats)
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/solo_b200.h"
+#include "solo_core.cuh"
+#include "solo_env.cuh"
+#include "solo_host_model.h"
+
+namespace solo {
+
+constexpr int kEnvsPerBlock = 32;
+constexpr int kLegThreads = 128;
+constexpr int kBlockThreads = 160;
+
+enum { MODE_STEP = 0, MODE_SETTLE = 1, MODE_SUBSTEP = 2 };
+
+struct DevArrays {
+  float* base;
+  float* q;
+  float* qd;
+  float* cforce;
+  float* hist;
+  EnvBook* book;
+  SoloEpisodeStats* stats;
+  /* reset cache: one row per settle count (settle_min + row) */
+  float* rc_base;    /* [K][16] */
+  float* rc_q;       /* [K][12] leg-major */
+  float* rc_qd;
+  float* rc_cforce;  /* [K][4] */
+  float* rc_hist;    /* [K][H][D0] */
+  int cap;
+};
+
+struct StepArgs {
+  DevArrays d;
+  SimConst sc;
+  ModelConst mc;
+  int n, mode;
+  int D0, D, A;
+  const float* in;   /* actions [n][A] (STEP) or joint torques [n][nj] (SUBSTEP) */
+  float* obs;
+  float* reward;
+  float* done;
+  uint32_t seed_lo, seed_hi;
+  long long env_id_offset;
+  float goal_radius;
+  int reset_simulate; /* 1: done envs restart from the reset pose with settle_left = k */
+  int force_settle;   /* >=0: cache generation, env i settles settle_min + i steps, goal far away */
+};
+
+struct ResetArgs {
+  DevArrays d;
+  SimConst sc;
+  int n, njl, D0, D;
+  const uint8_t* mask;
+  float* obs;
+  uint32_t seed_lo, seed_hi;
+  long long env_id_offset;
+  float goal_radius;
+  int reset_simulate, force_settle;
+};
+
+struct Smem {
+  float B[kRows * kRows][kEnvsPerBlock];
+  float g0[kRows][kEnvsPerBlock];
+  float lam[kRows][kEnvsPerBlock];
+  unsigned mask[kEnvsPerBlock];
+  LegConst leg[4];
+};
+
+__device__ __forceinline__ float sum4(float x) {
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  x += __shfl_xor_sync(0xffffffffu, x, 2);
+  return x;
+}
+__device__ __forceinline__ void sum4_sym6(Sym6& I) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) I.A[i] = sum4(I.A[i]);
+#pragma unroll
+  for (int i = 0; i < 9; i++) I.H[i] = sum4(I.H[i]);
+#pragma unroll
+  for (int i = 0; i < 6; i++) I.M[i] = sum4(I.M[i]);
+}
+
+/* ---- the pieces of one D0-row of the observation that a lane produces -------------- */
+template <int NJL>
+struct RowPieces {
+  float base[10], pg[4], qn[NJL], qdn[NJL], flag;
+};
+template <int NJL>
+__device__ __forceinline__ void make_pieces(const SimConst& sc, const BaseState& st, const Lane<NJL>& ln,
+                                            float cforce, const float* goal, RowPieces<NJL>& r) {
+  cur_base(st, r.base);
+#pragma unroll
+  for (int k = 0; k < NJL; k++) { r.qn[k] = ln.q[k] / sc.q_limit; r.qdn[k] = ln.qd[k] / sc.qd_limit; }
+  r.flag = contact_flag(sc, cforce);
+  if (sc.task == 2) cur_pointgoal(st, goal, r.pg);
+  else { r.pg[0] = r.pg[1] = r.pg[2] = r.pg[3] = 0.f; }
+}
+template <int NJL>
+__device__ __forceinline__ void store_pieces(float* row, int leg, int task, const RowPieces<NJL>& r) {
+#pragma unroll
+  for (int k = 0; k < NJL; k++) { row[idx_q(NJL, leg, k)] = r.qn[k]; row[idx_qd(NJL, leg, k)] = r.qdn[k]; }
+  row[idx_flag(NJL, leg)] = r.flag;
+  if (leg == 0) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) row[i] = r.base[i];
+    if (task == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) row[idx_pg(NJL) + i] = r.pg[i];
+    }
+  }
+}
+template <int NJL>
+__device__ __forceinline__ void load_pieces(const float* row, int leg, int task, RowPieces<NJL>& r) {
+#pragma unroll
+  for (int k = 0; k < NJL; k++) { r.qn[k] = row[idx_q(NJL, leg, k)]; r.qdn[k] = row[idx_qd(NJL, leg, k)]; }
+  r.flag = row[idx_flag(NJL, leg)];
+  if (leg == 0) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.base[i] = row[i];
+    if (task == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) r.pg[i] = row[idx_pg(NJL) + i];
+    }
+  }
+}
+template <int NJL>
+__device__ __forceinline__ void diff_pieces(const RowPieces<NJL>& a, const RowPieces<NJL>& b, RowPieces<NJL>& o) {
+#pragma unroll
+  for (int i = 0; i < 10; i++) o.base[i] = a.base[i] - b.base[i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) o.pg[i] = a.pg[i] - b.pg[i];
+#pragma unroll
+  for (int k = 0; k < NJL; k++) { o.qn[k] = a.qn[k] - b.qn[k]; o.qdn[k] = a.qdn[k] - b.qdn[k]; }
+  o.flag = a.flag - b.flag;
+}
+
+__device__ __forceinline__ float* hist_row(const DevArrays& d, int D0, int h, int e) {
+  return d.hist + ((size_t)h * d.cap + e) * D0;
+}
+
+/* deque(maxlen=H).append(get_current_state()) (solo.py:262) */
+template <int NJL>
+__device__ __forceinline__ void push_history(const DevArrays& d, const SimConst& sc, int D0, int e, int leg,
+                                             const RowPieces<NJL>& cur) {
+  for (int h = sc.H - 1; h > 0; h--) {
+    RowPieces<NJL> t;
+    load_pieces<NJL>(hist_row(d, D0, h - 1, e), leg, sc.task, t);
+    store_pieces<NJL>(hist_row(d, D0, h, e), leg, sc.task, t);
+  }
+  if (sc.H > 0) store_pieces<NJL>(hist_row(d, D0, 0, e), leg, sc.task, cur);
+}
+
+/* calc_state (solo.py:186-196): [cur, cur - hist[0], cur - hist[1], ...] */
+template <int NJL>
+__device__ __forceinline__ void write_obs(const DevArrays& d, const SimConst& sc, int D0, int D, int e, int leg,
+                                          const RowPieces<NJL>& cur, float* obs) {
+  float* row = obs + (size_t)e * D;
+  store_pieces<NJL>(row, leg, sc.task, cur);
+  for (int h = 0; h < sc.H; h++) {
+    RowPieces<NJL> old, df;
+    load_pieces<NJL>(hist_row(d, D0, h, e), leg, sc.task, old);
+    diff_pieces<NJL>(cur, old, df);
+    store_pieces<NJL>(row + (size_t)(1 + h) * D0, leg, sc.task, df);
+  }
+}
+
+__device__ __forceinline__ void env_rng(uint32_t seed_lo, uint32_t seed_hi, long long gid, EnvBook& bk, uint32_t* w) {
+  w[0] = (uint32_t)((unsigned long long)gid & 0xffffffffull);
+  w[1] = (uint32_t)((unsigned long long)gid >> 32);
+  w[2] = bk.episode;
+  w[3] = bk.draw++;
+  philox4x32_10(w, seed_lo, seed_hi);
+}
+
+__device__ __forceinline__ void load_base(const float* base, int e, BaseState& st, float* goal, float& potential) {
+  const float4* b = reinterpret_cast<const float4*>(base + (size_t)e * kBaseStride);
+  float4 b0 = b[0], b1 = b[1], b2 = b[2], b3 = b[3];
+  st.p[0] = b0.x; st.p[1] = b0.y; st.p[2] = b0.z;
+  st.q[0] = b0.w; st.q[1] = b1.x; st.q[2] = b1.y; st.q[3] = b1.z;
+  st.v[0] = b1.w; st.v[1] = b2.x; st.v[2] = b2.y;
+  st.w[0] = b2.z; st.w[1] = b2.w; st.w[2] = b3.x;
+  goal[0] = b3.y; goal[1] = b3.z; potential = b3.w;
+}
+__device__ __forceinline__ void store_base(float* base, int e, const BaseState& st, const float* goal, float potential) {
+  float4* b = reinterpret_cast<float4*>(base + (size_t)e * kBaseStride);
+  b[0] = make_float4(st.p[0], st.p[1], st.p[2], st.q[0]);
+  b[1] = make_float4(st.q[1], st.q[2], st.q[3], st.v[0]);
+  b[2] = make_float4(st.v[1], st.v[2], st.w[0], st.w[1]);
+  b[3] = make_float4(st.w[2], goal[0], goal[1], potential);
+}
+
+/* SoloBaseEnv.reset up to (not including) the settle loop (baseEnv.py:70-77, solo.py:166-181),
+ * or — cached mode — the memoised result of the whole reset for the drawn settle count. */
+template <int NJL>
+__device__ __forceinline__ void begin_reset(const DevArrays& d, const SimConst& sc, int D0, int e, int leg,
+                                            long long gid, uint32_t seed_lo, uint32_t seed_hi, float goal_radius,
+                                            int reset_simulate, int force_settle, BaseState& st, Lane<NJL>& ln,
+                                            float& cforce, float* goal, float& potential, EnvBook& bk) {
+  bk.episode += 1; bk.draw = 0;
+  uint32_t w[4];
+  env_rng(seed_lo, seed_hi, gid, bk, w);
+  if (sc.task == 2) sample_goal(w, goal_radius, goal);          /* solo.py:173-174 */
+  int k = sc.settle_min + (sc.settle_span > 0 ? (int)(w[0] % (uint32_t)sc.settle_span) : 0); /* baseEnv.py:79 */
+  if (force_settle >= 0) { k = sc.settle_min + (e % (sc.settle_span > 0 ? sc.settle_span : 1)); goal[0] = 1.0e3f; goal[1] = 1.0e3f; }
+  book_clear_episode(bk);
+  bk.goals = 0;
+  if (reset_simulate) {
+    reset_pose(sc, st);
+#pragma unroll
+    for (int j = 0; j < NJL; j++) { ln.q[j] = 0.f; ln.qd[j] = 0.f; }
+    cforce = -1.0f;                                              /* contact set cleared */
+    RowPieces<NJL> cur;
+    make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
+    for (int h = 0; h < sc.H; h++) store_pieces<NJL>(hist_row(d, D0, h, e), leg, sc.task, cur); /* solo.py:170-171 */
+    bk.settle_left = k;
+  } else {
+    const int row = k - sc.settle_min;
+    float g2[2], pot;
+    load_base(d.rc_base, row, st, g2, pot);
+#pragma unroll
+    for (int j = 0; j < NJL; j++) {
+      ln.q[j] = d.rc_q[row * 12 + leg * NJL + j];
+      ln.qd[j] = d.rc_qd[row * 12 + leg * NJL + j];
+    }
+    cforce = d.rc_cforce[row * 4 + leg];
+    for (int h = 0; h < sc.H; h++) {
+      RowPieces<NJL> t;
+      load_pieces<NJL>(d.rc_hist + ((size_t)row * sc.H + h) * D0, leg, sc.task, t);
+      t.pg[2] = goal[0] / 2.0f; t.pg[3] = goal[1] / 2.0f;
+      store_pieces<NJL>(hist_row(d, D0, h, e), leg, sc.task, t);
+    }
+    bk.settle_left = 0;
+  }
+  potential = (sc.task == 2) ? calc_potential(st, goal) : 0.f;   /* solo.py:176 */
+}
+
+/* One Bullet-equivalent substep for the four lanes of an env (see solo_core.cuh). */
+template <int NJL>
+__device__ __forceinline__ void group_substep(Smem& sm, const ModelConst& mc, const SimConst& sc, int el, int leg,
+                                              BaseState& st, Lane<NJL>& ln, const float* tau, float& cforce) {
+  const LegConst& lc = sm.leg[leg];
+  BaseWork bw;
+  base_prepare(st, bw);
+  Sym6 IA;
+  float pA[6], a0[6];
+  leg_inward<NJL>(lc, sc, bw, ln, tau, IA, pA);
+  sum4_sym6(IA);
+#pragma unroll
+  for (int i = 0; i < 6; i++) pA[i] = sum4(pA[i]);
+  base_solve(mc, sc, bw, IA, pA, a0);
+  {
+    float qdd[NJL], aw[3], al[3];
+    leg_outward<NJL>(ln, a0, qdd);
+    base_world_acc(sc, bw, a0, aw, al);
+    base_add_velocity(sc, st, aw, al, sc.dt);
+#pragma unroll
+    for (int k = 0; k < NJL; k++) ln.qd[k] = clampf(ln.qd[k] + sc.dt * qdd[k], -sc.vmax, sc.vmax);
+  }
+  contact_setup<NJL>(lc, mc, sc, st, bw, ln);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned gbase = lane & ~3u;
+  unsigned amask = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) amask |= (unsigned)(__shfl_sync(0xffffffffu, ln.active, gbase + j) != 0) << j;
+  if (__any_sync(0xffffffffu, amask != 0)) {
+    float rows[3][kRows];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float Kj[3][6];
+#pragma unroll
+      for (int n = 0; n < 3; n++) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) Kj[n][i] = __shfl_sync(0xffffffffu, ln.K[n][i], gbase + j);
+      }
+      assemble_block<NJL>(ln, j, Kj, rows);
+    }
+    assemble_finish<NJL>(ln, leg, rows, amask, &sm.B[0][el], &sm.g0[0][el], kEnvsPerBlock);
+  }
+  if (leg == 0) sm.mask[el] = amask;
+  const int any = __syncthreads_or(amask != 0);
+  float lam3[3] = {0.f, 0.f, 0.f};
+  if (any) {
+    __syncthreads();   /* solver warp runs pgs_solve between the two barriers */
+#pragma unroll
+    for (int m = 0; m < 3; m++) lam3[m] = amask ? sm.lam[row_of(leg, m)][el] : 0.f;
+  }
+  if (any) { /* block-uniform: envs without contact add exact zeros (full-mask shuffles inside) */
+    float part[6], dv0[6];
+    impulse_base_part<NJL>(ln, lam3, part);
+#pragma unroll
+    for (int i = 0; i < 6; i++) dv0[i] = sum4(part[i]);
+    impulse_leg<NJL>(ln, sc, lam3, dv0);
+    float dw[3], dvl[3];
+    mat3_mulv(bw.R, dv0, dw);
+    mat3_mulv(bw.R, dv0 + 3, dvl);
+    base_add_velocity(sc, st, dw, dvl, 1.0f);
+  }
+  cforce = ln.active ? lam3[0] * sc.inv_dt : -1.0f;
+  integrate_base(sc, st);
+#pragma unroll
+  for (int k = 0; k < NJL; k++) ln.q[k] += sc.dt * ln.qd[k];
+}
+
+template <int NJL>
+__global__ void __launch_bounds__(kBlockThreads) step_kernel(const __grid_constant__ StepArgs args) {
+  __shared__ Smem sm;
+  const int tid = threadIdx.x;
+  const SimConst& sc = args.sc;
+  {
+    const float* src = reinterpret_cast<const float*>(&args.mc.leg[0]);
+    float* dst = reinterpret_cast<float*>(&sm.leg[0]);
+    for (int i = tid; i < (int)(sizeof(LegConst) * 4 / sizeof(float)); i += kBlockThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int nsub = (args.mode == MODE_SUBSTEP) ? 1 : sc.frame_skip;
+
+  if (tid >= kLegThreads) { /* ---- solver warp: one env per lane ---- */
+    const int lane = tid - kLegThreads;
+    for (int s = 0; s < nsub; s++) {
+      const int any = __syncthreads_or(0);
+      if (any) {
+        const unsigned fm = __reduce_or_sync(0xffffffffu, sm.mask[lane]);
+        pgs_solve(&sm.B[0][lane], &sm.g0[0][lane], kEnvsPerBlock, sc.iters, sc.cone, sc.mu, fm, &sm.lam[0][lane]);
+        __syncthreads();
+      }
+    }
+    return;
+  }
+
+  /* ---- leg lanes ---- */
+  const DevArrays& d = args.d;
+  const int el = tid >> 2, leg = tid & 3;
+  const int env = blockIdx.x * kEnvsPerBlock + el;
+  const bool valid = env < args.n;
+  const int e = valid ? env : args.n - 1;
+  const long long gid = args.env_id_offset + e;
+  const int D0 = args.D0;
+
+  BaseState st;
+  float goal[2], potential;
+  load_base(d.base, e, st, goal, potential);
+  Lane<NJL> ln;
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    ln.q[k] = d.q[((size_t)k * d.cap + e) * 4 + leg];
+    ln.qd[k] = d.qd[((size_t)k * d.cap + e) * 4 + leg];
+  }
+  float cforce = d.cforce[e * 4 + leg];
+  EnvBook bk = d.book[e];
+  const bool active = valid && (args.mode != MODE_SETTLE || bk.settle_left > 0);
+
+  float tau[NJL], act[NJL];
+#pragma unroll
+  for (int k = 0; k < NJL; k++) { tau[k] = 0.f; act[k] = 0.f; }
+  if (args.mode == MODE_STEP) {                     /* apply_action (solo.py:224-259) */
+    const float* a = args.in + (size_t)e * args.A;
+    float kp = sc.kp, kd = sc.kd;
+    if (sc.control == 2) { kp = a[4 * NJL]; kd = a[4 * NJL + 1]; }
+#pragma unroll
+    for (int k = 0; k < NJL; k++) {
+      act[k] = a[leg * NJL + k];
+      tau[k] = action_to_torque(sc, act[k], ln.q[k], ln.qd[k], kp, kd);
+    }
+  } else if (args.mode == MODE_SUBSTEP) {
+#pragma unroll
+    for (int k = 0; k < NJL; k++) tau[k] = args.in[(size_t)e * 4 * NJL + leg * NJL + k];
+  }
+
+  if (args.mode != MODE_SUBSTEP && active) {        /* simulator_step: history push (solo.py:262) */
+    RowPieces<NJL> cur;
+    make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
+    push_history<NJL>(d, sc, D0, e, leg, cur);
+  }
+
+  for (int s = 0; s < nsub; s++) {                  /* frame_skip x p.stepSimulation() (solo.py:264-265) */
+    const bool torque_on = (s == 0) || sc.torque_hold; /* SURVEY F4 */
+    float tau_s[NJL];
+#pragma unroll
+    for (int k = 0; k < NJL; k++) tau_s[k] = torque_on ? tau[k] : 0.f;
+    group_substep<NJL>(sm, args.mc, sc, el, leg, st, ln, tau_s, cforce);
+  }
+
+  float progress = 0.f;
+  if (args.mode != MODE_SUBSTEP && sc.task == 2) {  /* pointgoal bookkeeping (solo.py:267-272) */
+    const float oldp = potential;
+    potential = calc_potential(st, goal);
+    progress = oldp - potential;
+    if (potential < sc.goal_reach) {
+      bk.goals += 1;
+      uint32_t w[4];
+      env_rng(args.seed_lo, args.seed_hi, gid, bk, w);
+      sample_goal(w, args.goal_radius, goal);
+    }
+  }
+
+  if (args.mode == MODE_STEP) {
+    bk.timestep += 1;                               /* baseEnv.py:47 */
+    RowPieces<NJL> cur;
+    make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
+    if (valid) write_obs<NJL>(d, sc, D0, args.D, e, leg, cur, args.obs);
+    float sq = 0.f, sa = 0.f;
+#pragma unroll
+    for (int k = 0; k < NJL; k++) {
+      sq += (sc.task == 0) ? fabsf(ln.q[k]) : ln.q[k] * ln.q[k];
+      sa += act[k] * act[k];
+    }
+    sq = sum4(sq); sa = sum4(sa);
+    StepOutcome o = step_outcome(sc, st, 4 * NJL, sq, sa, progress, bk);
+    if (valid && leg == 0) {
+      args.reward[e] = o.reward;
+      args.done[e] = o.done ? 1.0f : 0.0f;
+    }
+    if (o.done) {
+      if (valid && leg == 0) {                      /* info dict (baseEnv.py:63-66) */
+        SoloEpisodeStats s;
+        s.episode_reward = o.reward; s.episode_return = bk.reward_sum;
+        s.episode_length = bk.timestep; s.success = o.success; s.timeout = o.timeout;
+        s.goals_reached = bk.goals_env;
+        s.dr_stand = bk.dr[0]; s.dr_joint_pose = bk.dr[1]; s.dr_torque = bk.dr[2];
+        s.dr_balance = bk.dr[3]; s.dr_progress = bk.dr[4];
+        d.stats[e] = s;
+      }
+      /* worker auto-reset (agents/ppo/envs.py:38-40) */
+      if (valid) {
+        begin_reset<NJL>(d, sc, D0, e, leg, gid, args.seed_lo, args.seed_hi, args.goal_radius,
+                         args.reset_simulate, -1, st, ln, cforce, goal, potential, bk);
+        if (!args.reset_simulate) {
+          make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
+          write_obs<NJL>(d, sc, D0, args.D, e, leg, cur, args.obs);
+        }
+      }
+    }
+  } else if (args.mode == MODE_SETTLE && active) {
+    bk.settle_left -= 1;
+    if (bk.settle_left == 0 && args.obs != nullptr) {
+      RowPieces<NJL> cur;
+      make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
+      write_obs<NJL>(d, sc, D0, args.D, e, leg, cur, args.obs);
+    }
+  }
+
+  if (active) {
+    if (leg == 0) { store_base(d.base, e, st, goal, potential); d.book[e] = bk; }
+#pragma unroll
+    for (int k = 0; k < NJL; k++) {
+      d.q[((size_t)k * d.cap + e) * 4 + leg] = ln.q[k];
+      d.qd[((size_t)k * d.cap + e) * 4 + leg] = ln.qd[k];
+    }
+    d.cforce[e * 4 + leg] = cforce;
+  }
+}
+
+/* VecEnvWrapper.reset (agents/ppo/envs.py:97-100): masked begin_reset, four lanes per env */
+template <int NJL>
+__global__ void reset_kernel(const __grid_constant__ ResetArgs args) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t >> 2, leg = t & 3;
+  if (e >= args.n) return;
+  if (args.mask != nullptr && args.mask[e] == 0) return;
+  const DevArrays& d = args.d;
+  BaseState st;
+  float goal[2], potential;
+  load_base(d.base, e, st, goal, potential);
+  Lane<NJL> ln;
+  float cforce;
+  EnvBook bk = d.book[e];
+  begin_reset<NJL>(d, args.sc, args.D0, e, leg, args.env_id_offset + e, args.seed_lo, args.seed_hi,
+                   args.goal_radius, args.reset_simulate, args.force_settle, st, ln, cforce, goal, potential, bk);
+  if (!args.reset_simulate && args.obs != nullptr) {
+    RowPieces<NJL> cur;
+    make_pieces<NJL>(args.sc, st, ln, cforce, goal, cur);
+    write_obs<NJL>(d, args.sc, args.D0, args.D, e, leg, cur, args.obs);
+  }
+  if (leg == 0) { store_base(d.base, e, st, goal, potential); d.book[e] = bk; }
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    d.q[((size_t)k * d.cap + e) * 4 + leg] = ln.q[k];
+    d.qd[((size_t)k * d.cap + e) * 4 + leg] = ln.qd[k];
+  }
+  d.cforce[e * 4 + leg] = cforce;
+}
+
+/* get_observation (agents/ppo/envs.py:102-105) */
+template <int NJL>
+__global__ void obs_kernel(DevArrays d, SimConst sc, int n, int D0, int D, float* obs) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t >> 2, leg = t & 3;
+  if (e >= n) return;
+  BaseState st;
+  float goal[2], potential;
+  load_base(d.base, e, st, goal, potential);
+  Lane<NJL> ln;
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    ln.q[k] = d.q[((size_t)k * d.cap + e) * 4 + leg];
+    ln.qd[k] = d.qd[((size_t)k * d.cap + e) * 4 + leg];
+  }
+  RowPieces<NJL> cur;
+  make_pieces<NJL>(sc, st, ln, d.cforce[e * 4 + leg], goal, cur);
+  write_obs<NJL>(d, sc, D0, D, e, leg, cur, obs);
+}
+
+/* state [n][13+2nj] <-> SoA */
+template <int NJL>
+__global__ void get_state_kernel(DevArrays d, int n, float* state) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t >> 2, leg = t & 3;
+  if (e >= n) return;
+  const int nj = 4 * NJL, W = 13 + 2 * nj;
+  float* s = state + (size_t)e * W;
+  if (leg == 0) {
+    for (int i = 0; i < 13; i++) s[i] = d.base[(size_t)e * kBaseStride + i];
+  }
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    s[13 + leg * NJL + k] = d.q[((size_t)k * d.cap + e) * 4 + leg];
+    s[13 + nj + leg * NJL + k] = d.qd[((size_t)k * d.cap + e) * 4 + leg];
+  }
+}
+template <int NJL>
+__global__ void set_state_kernel(DevArrays d, SimConst sc, int n, int D0, const float* state) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t >> 2, leg = t & 3;
+  if (e >= n) return;
+  const int nj = 4 * NJL, W = 13 + 2 * nj;
+  const float* s = state + (size_t)e * W;
+  BaseState st;
+  float goal[2], potential;
+  load_base(d.base, e, st, goal, potential);
+  for (int i = 0; i < 3; i++) { st.p[i] = s[i]; st.v[i] = s[7 + i]; st.w[i] = s[10 + i]; }
+  for (int i = 0; i < 4; i++) st.q[i] = s[3 + i];
+  Lane<NJL> ln;
+#pragma unroll
+  for (int k = 0; k < NJL; k++) { ln.q[k] = s[13 + leg * NJL + k]; ln.qd[k] = s[13 + nj + leg * NJL + k]; }
+  const float cforce = -1.0f;
+  RowPieces<NJL> cur;
+  make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
+  for (int h = 0; h < sc.H; h++) store_pieces<NJL>(hist_row(d, D0, h, e), leg, sc.task, cur);
+  potential = (sc.task == 2) ? calc_potential(st, goal) : 0.f;
+  if (leg == 0) {
+    store_base(d.base, e, st, goal, potential);
+    EnvBook bk = d.book[e];
+    book_clear_episode(bk);
+    bk.settle_left = 0;
+    d.book[e] = bk;
+  }
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    d.q[((size_t)k * d.cap + e) * 4 + leg] = ln.q[k];
+    d.qd[((size_t)k * d.cap + e) * 4 + leg] = ln.qd[k];
+  }
+  d.cforce[e * 4 + leg] = cforce;
+}
+
+__global__ void set_goal_kernel(DevArrays d, int n, const float* goals) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float* b = d.base + (size_t)e * kBaseStride;
+  b[kBaseGoal] = goals[2 * e]; b[kBaseGoal + 1] = goals[2 * e + 1];
+  float dx = b[0] - goals[2 * e], dy = b[1] - goals[2 * e + 1];
+  b[kBasePot] = sqrtf(dx * dx + dy * dy);
+}
+
+__global__ void contacts_kernel(DevArrays d, SimConst sc, int n, float* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 4) return;
+  const float f = d.cforce[t];
+  out[t * 3 + 0] = contact_flag(sc, f);
+  out[t * 3 + 1] = f >= 0.f ? 1.f : 0.f;
+  out[t * 3 + 2] = f >= 0.f ? f : 0.f;
+}
+
+/* contact-free forward dynamics on caller-provided states (test hook) */
+template <int NJL>
+__global__ void fd_kernel(ModelConst mc, SimConst sc, int n, const float* state, const float* tau_in, float* out) {
+  __shared__ LegConst sleg[4];
+  {
+    const float* src = reinterpret_cast<const float*>(&mc.leg[0]);
+    float* dst = reinterpret_cast<float*>(&sleg[0]);
+    for (int i = threadIdx.x; i < (int)(sizeof(LegConst) * 4 / sizeof(float)); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int env = t >> 2, leg = t & 3;
+  const int e = env < n ? env : n - 1;
+  const int nj = 4 * NJL, W = 13 + 2 * nj;
+  const float* s = state + (size_t)e * W;
+  BaseState st;
+  for (int i = 0; i < 3; i++) { st.p[i] = s[i]; st.v[i] = s[7 + i]; st.w[i] = s[10 + i]; }
+  for (int i = 0; i < 4; i++) st.q[i] = s[3 + i];
+  Lane<NJL> ln;
+  float tau[NJL];
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    ln.q[k] = s[13 + leg * NJL + k]; ln.qd[k] = s[13 + nj + leg * NJL + k];
+    tau[k] = tau_in[(size_t)e * nj + leg * NJL + k];
+  }
+  BaseWork bw;
+  base_prepare(st, bw);
+  Sym6 IA;
+  float pA[6], a0[6], qdd[NJL], aw[3], al[3];
+  leg_inward<NJL>(sleg[leg], sc, bw, ln, tau, IA, pA);
+  sum4_sym6(IA);
+#pragma unroll
+  for (int i = 0; i < 6; i++) pA[i] = sum4(pA[i]);
+  base_solve(mc, sc, bw, IA, pA, a0);
+  leg_outward<NJL>(ln, a0, qdd);
+  base_world_acc(sc, bw, a0, aw, al);
+  if (env < n) {
+    float* o = out + (size_t)e * (6 + nj);
+    if (leg == 0) { for (int i = 0; i < 3; i++) { o[i] = aw[i]; o[3 + i] = al[i]; } }
+#pragma unroll
+    for (int k = 0; k < NJL; k++) o[6 + leg * NJL + k] = qdd[k];
+  }
+}
+
+template <int NJL>
+__global__ void torque_kernel(DevArrays d, SimConst sc, int n, int A, const float* actions, float* tau) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t >> 2, leg = t & 3;
+  if (e >= n) return;
+  const float* a = actions + (size_t)e * A;
+  float kp = sc.kp, kd = sc.kd;
+  if (sc.control == 2) { kp = a[4 * NJL]; kd = a[4 * NJL + 1]; }
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    float q = d.q[((size_t)k * d.cap + e) * 4 + leg], qd = d.qd[((size_t)k * d.cap + e) * 4 + leg];
+    tau[(size_t)e * 4 * NJL + leg * NJL + k] = action_to_torque(sc, a[leg * NJL + k], q, qd, kp, kd);
+  }
+}
+
+/* copy env rows 0..K-1 into the reset cache */
+template <int NJL>
+__global__ void fill_cache_kernel(DevArrays d, int K, int H, int D0) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= K) return;
+  for (int i = 0; i < kBaseStride; i++) d.rc_base[t * kBaseStride + i] = d.base[(size_t)t * kBaseStride + i];
+  for (int leg = 0; leg < 4; leg++) {
+    for (int k = 0; k < NJL; k++) {
+      d.rc_q[t * 12 + leg * NJL + k] = d.q[((size_t)k * d.cap + t) * 4 + leg];
+      d.rc_qd[t * 12 + leg * NJL + k] = d.qd[((size_t)k * d.cap + t) * 4 + leg];
+    }
+    d.rc_cforce[t * 4 + leg] = d.cforce[t * 4 + leg];
+  }
+  for (int h = 0; h < H; h++)
+    for (int i = 0; i < D0; i++) d.rc_hist[((size_t)t * H + h) * D0 + i] = d.hist[((size_t)h * d.cap + t) * D0 + i];
+}
+
+/* Reverse-scan GAE (agents/ppo/storage.py:35-55): one thread per env walks t = T-1..0;
+ * consecutive threads read consecutive words of every [t] row, 20 B per (t, env). */
+__global__ void gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                           const float* __restrict__ masks, float* __restrict__ returns, int T, int N,
+                           float gamma, float lam, int use_gae) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (use_gae) {
+    float gae = 0.f;
+    float v_next = values[(size_t)T * N + n];
+    for (int t = T - 1; t >= 0; t--) {
+      const float m = masks[(size_t)(t + 1) * N + n];
+      const float v = values[(size_t)t * N + n];
+      const float delta = rewards[(size_t)t * N + n] + gamma * v_next * m - v;
+      gae = delta + gamma * lam * m * gae;
+      returns[(size_t)t * N + n] = gae + v;
+      v_next = v;
+    }
+  } else {
+    float ret = returns[(size_t)T * N + n];
+    for (int t = T - 1; t >= 0; t--) {
+      ret = ret * gamma * masks[(size_t)(t + 1) * N + n] + rewards[(size_t)t * N + n];
+      returns[(size_t)t * N + n] = ret;
+    }
+  }
+}
+
+}  // namespace solo
+
+/* ===================================================================== C-ABI */
+using namespace solo;
+
+struct SoloHandle {
+  SoloModelTable model;
+  SoloSimParams params;
+  ModelConst mc;
+  SimConst sc;
+  int n, njl, nj, A, D0, D, device, K, cap;
+  uint64_t seed;
+  long long env_id_offset;
+  float goal_radius;
+  DevArrays d;
+  bool was_reset;
+  long long launches;
+  std::string err;
+  /* staging for solo_step_host */
+  float *s_act, *s_obs, *s_rew, *s_done;
+};
+
+static thread_local std::string g_err;
+
+static int fail(SoloHandle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(h, call)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) return fail(h, SOLO_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+static StepArgs make_step_args(SoloHandle* h, int mode, int n, const float* in, float* obs, float* rew, float* done) {
+  StepArgs a;
+  a.d = h->d; a.sc = h->sc; a.mc = h->mc; a.n = n; a.mode = mode;
+  a.D0 = h->D0; a.D = h->D; a.A = h->A;
+  a.in = in; a.obs = obs; a.reward = rew; a.done = done;
+  a.seed_lo = (uint32_t)(h->seed & 0xffffffffu); a.seed_hi = (uint32_t)(h->seed >> 32);
+  a.env_id_offset = h->env_id_offset; a.goal_radius = h->goal_radius;
+  a.reset_simulate = (h->params.reset_mode == SOLO_RESET_SIMULATE);
+  a.force_settle = -1;
+  return a;
+}
+static void launch_step(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
+  const int blocks = (a.n + kEnvsPerBlock - 1) / kEnvsPerBlock;
+  if (h->njl == 3) step_kernel<3><<<blocks, kBlockThreads, 0, s>>>(a);
+  else step_kernel<2><<<blocks, kBlockThreads, 0, s>>>(a);
+  h->launches++;
+}
+static ResetArgs make_reset_args(SoloHandle* h, int n, const uint8_t* mask, float* obs) {
+  ResetArgs a;
+  a.d = h->d; a.sc = h->sc; a.n = n; a.njl = h->njl; a.D0 = h->D0; a.D = h->D;
+  a.mask = mask; a.obs = obs;
+  a.seed_lo = (uint32_t)(h->seed & 0xffffffffu); a.seed_hi = (uint32_t)(h->seed >> 32);
+  a.env_id_offset = h->env_id_offset; a.goal_radius = h->goal_radius;
+  a.reset_simulate = (h->params.reset_mode == SOLO_RESET_SIMULATE);
+  a.force_settle = -1;
+  return a;
+}
+static void launch_reset(SoloHandle* h, const ResetArgs& a, cudaStream_t s) {
+  const int threads = 128, blocks = (a.n * 4 + threads - 1) / threads;
+  if (h->njl == 3) reset_kernel<3><<<blocks, threads, 0, s>>>(a);
+  else reset_kernel<2><<<blocks, threads, 0, s>>>(a);
+  h->launches++;
+}
+/* the settle loop of SoloBaseEnv.reset (baseEnv.py:79-80), simulate mode: the longest settle
+ * count bounds the number of launches; envs that are done settling idle */
+static void launch_settle(SoloHandle* h, int n, float* obs, cudaStream_t s) {
+  const int kmax = h->params.settle_max - 1;
+  for (int i = 0; i < kmax; i++) {
+    StepArgs a = make_step_args(h, MODE_SETTLE, n, nullptr, obs, nullptr, nullptr);
+    launch_step(h, a, s);
+  }
+}
+
+extern "C" {
+
+int solo_default_params(SoloSimParams* p) {
+  if (!p) return fail(nullptr, SOLO_E_ARG, "null params");
+  fill_default_params(p);
+  return SOLO_OK;
+}
+
+int solo_dims(const SoloModelTable* m, const SoloSimParams* p, int32_t* nj, int32_t* act_dim,
+              int32_t* obs_dim0, int32_t* obs_dim) {
+  if (!m || !p) return fail(nullptr, SOLO_E_ARG, "null argument");
+  int n = 0;
+  for (int i = 0; i < m->num_links; i++) n += (m->jtype[i] == SOLO_JOINT_REVOLUTE);
+  const int d0 = 1 + 3 + 6 + 2 * n + 4 + (p->task == SOLO_TASK_POINTGOAL ? 4 : 0);
+  if (nj) *nj = n;
+  if (act_dim) *act_dim = n + (p->control == SOLO_CONTROL_VPD ? 2 : 0);
+  if (obs_dim0) *obs_dim0 = d0;
+  if (obs_dim) *obs_dim = d0 * (1 + p->num_history_stack);
+  return SOLO_OK;
+}
+
+const char* solo_last_error(const SoloHandle* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int solo_destroy(SoloHandle* h) {
+  if (!h) return SOLO_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d.base); cudaFree(h->d.q); cudaFree(h->d.qd); cudaFree(h->d.cforce); cudaFree(h->d.hist);
+  cudaFree(h->d.book); cudaFree(h->d.stats);
+  cudaFree(h->d.rc_base); cudaFree(h->d.rc_q); cudaFree(h->d.rc_qd); cudaFree(h->d.rc_cforce); cudaFree(h->d.rc_hist);
+  cudaFree(h->s_act); cudaFree(h->s_obs); cudaFree(h->s_rew); cudaFree(h->s_done);
+  delete h;
+  return SOLO_OK;
+}
+
+int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_t num_envs, int32_t device,
+                uint64_t seed, int64_t env_id_offset, SoloHandle** out) {
+  if (!model || !params || !out || num_envs <= 0) return fail(nullptr, SOLO_E_ARG, "bad argument to solo_create");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(nullptr, SOLO_E_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(nullptr, SOLO_E_ARG, "bad device index");
+  SoloHandle* h = new SoloHandle();
+  h->model = *model; h->params = *params;
+  std::string err;
+  int rc = build_model_const(*model, h->mc, err);
+  if (rc == SOLO_OK) rc = build_sim_const(*params, h->sc, err);
+  if (rc == SOLO_OK && params->num_history_stack > 8) { rc = SOLO_E_ARG; err = "num_history_stack > 8"; }
+  if (rc != SOLO_OK) { delete h; return fail(nullptr, rc, err); }
+  h->n = num_envs; h->njl = h->mc.njl; h->nj = 4 * h->njl;
+  h->A = h->nj + (params->control == SOLO_CONTROL_VPD ? 2 : 0);
+  h->D0 = obs_dim0(h->njl, params->task);
+  h->D = h->D0 * (1 + params->num_history_stack);
+  h->device = device; h->seed = seed; h->env_id_offset = env_id_offset;
+  h->goal_radius = (float)params->goal_radius;
+  h->was_reset = false; h->launches = 0;
+  h->K = params->settle_max - params->settle_min; if (h->K < 1) h->K = 1;
+  h->cap = num_envs > h->K ? num_envs : h->K;
+  h->s_act = h->s_obs = h->s_rew = h->s_done = nullptr;
+  memset(&h->d, 0, sizeof(h->d));
+  h->d.cap = h->cap;
+  const int H = params->num_history_stack;
+  CUDA_TRY(h, cudaSetDevice(device));
+  const size_t cap = (size_t)h->cap;
+  CUDA_TRY(h, cudaMalloc(&h->d.base, cap * kBaseStride * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d.q, cap * 4 * h->njl * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d.qd, cap * 4 * h->njl * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d.cforce, cap * 4 * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d.hist, (cap * (H > 0 ? H : 1)) * h->D0 * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d.book, cap * sizeof(EnvBook)));
+  CUDA_TRY(h, cudaMalloc(&h->d.stats, cap * sizeof(SoloEpisodeStats)));
+  CUDA_TRY(h, cudaMalloc(&h->d.rc_base, (size_t)h->K * kBaseStride * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d.rc_q, (size_t)h->K * 12 * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d.rc_qd, (size_t)h->K * 12 * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d.rc_cforce, (size_t)h->K * 4 * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d.rc_hist, (size_t)h->K * (H > 0 ? H : 1) * h->D0 * sizeof(float)));
+  CUDA_TRY(h, cudaMemset(h->d.base, 0, cap * kBaseStride * sizeof(float)));
+  CUDA_TRY(h, cudaMemset(h->d.q, 0, cap * 4 * h->njl * sizeof(float)));
+  CUDA_TRY(h, cudaMemset(h->d.qd, 0, cap * 4 * h->njl * sizeof(float)));
+  CUDA_TRY(h, cudaMemset(h->d.cforce, 0, cap * 4 * sizeof(float)));
+  CUDA_TRY(h, cudaMemset(h->d.hist, 0, (cap * (H > 0 ? H : 1)) * h->D0 * sizeof(float)));
+  CUDA_TRY(h, cudaMemset(h->d.book, 0, cap * sizeof(EnvBook)));
+  CUDA_TRY(h, cudaMemset(h->d.stats, 0, cap * sizeof(SoloEpisodeStats)));
+
+  /* Reset cache: the reset trajectory (fixed pose, zero torque, k control steps) depends only
+   * on k, so it is simulated ONCE per k with the very kernel that simulate-mode resets use
+   * (same binary code => the cached rows are bit-identical to simulating them), and a
+   * reset during stepping becomes a table lookup. */
+  {
+    cudaStream_t s = 0;
+    ResetArgs ra = make_reset_args(h, h->K, nullptr, nullptr);
+    ra.reset_simulate = 1; ra.force_settle = 1;
+    launch_reset(h, ra, s);
+    const int kmax = params->settle_max - 1;
+    for (int i = 0; i < kmax; i++) {
+      StepArgs a = make_step_args(h, MODE_SETTLE, h->K, nullptr, nullptr, nullptr, nullptr);
+      a.reset_simulate = 1;
+      launch_step(h, a, s);
+    }
+    if (h->njl == 3) fill_cache_kernel<3><<<1, 32, 0, s>>>(h->d, h->K, H, h->D0);
+    else fill_cache_kernel<2><<<1, 32, 0, s>>>(h->d, h->K, H, h->D0);
+    h->launches++;
+    CUDA_TRY(h, cudaMemsetAsync(h->d.book, 0, cap * sizeof(EnvBook), s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  *out = h;
+  return SOLO_OK;
+}
+
+int solo_reset(SoloHandle* h, const uint8_t* d_mask, float* d_obs_out, void* stream) {
+  if (!h) return fail(nullptr, SOLO_E_ARG, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  ResetArgs ra = make_reset_args(h, h->n, d_mask, d_obs_out);
+  launch_reset(h, ra, s);
+  if (ra.reset_simulate) launch_settle(h, h->n, d_obs_out, s);
+  if (d_mask == nullptr) h->was_reset = true;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_step(SoloHandle* h, const float* d_actions, float* d_obs, float* d_reward, float* d_done, void* stream) {
+  if (!h || !d_actions || !d_obs || !d_reward || !d_done) return fail(h, SOLO_E_ARG, "null argument to solo_step");
+  if (!h->was_reset) return fail(h, SOLO_E_STATE, "env.reset() must be called before step"); /* baseEnv.py:43 */
+  cudaStream_t s = (cudaStream_t)stream;
+  StepArgs a = make_step_args(h, MODE_STEP, h->n, d_actions, d_obs, d_reward, d_done);
+  launch_step(h, a, s);
+  if (a.reset_simulate) launch_settle(h, h->n, d_obs, s);
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_step_host(SoloHandle* h, const float* h_actions, float* h_obs, float* h_reward, float* h_done, void* stream) {
+  if (!h || !h_actions || !h_obs || !h_reward || !h_done) return fail(h, SOLO_E_ARG, "null argument to solo_step_host");
+  if (!h->was_reset) return fail(h, SOLO_E_STATE, "env.reset() must be called before step");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)h->n;
+  if (!h->s_act) {
+    CUDA_TRY(h, cudaMalloc(&h->s_act, n * h->A * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&h->s_obs, n * h->D * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&h->s_rew, n * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&h->s_done, n * sizeof(float)));
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->s_act, h_actions, n * h->A * sizeof(float), cudaMemcpyHostToDevice, s));
+  int rc = solo_step(h, h->s_act, h->s_obs, h->s_rew, h->s_done, stream);
+  if (rc != SOLO_OK) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h_obs, h->s_obs, n * h->D * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h_reward, h->s_rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaMemcpyAsync(h_done, h->s_done, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  return SOLO_OK;
+}
+
+int solo_get_observation(SoloHandle* h, float* d_obs, void* stream) {
+  if (!h || !d_obs) return fail(h, SOLO_E_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int threads = 128, blocks = (h->n * 4 + threads - 1) / threads;
+  if (h->njl == 3) obs_kernel<3><<<blocks, threads, 0, s>>>(h->d, h->sc, h->n, h->D0, h->D, d_obs);
+  else obs_kernel<2><<<blocks, threads, 0, s>>>(h->d, h->sc, h->n, h->D0, h->D, d_obs);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_get_state(SoloHandle* h, float* d_state, void* stream) {
+  if (!h || !d_state) return fail(h, SOLO_E_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int threads = 128, blocks = (h->n * 4 + threads - 1) / threads;
+  if (h->njl == 3) get_state_kernel<3><<<blocks, threads, 0, s>>>(h->d, h->n, d_state);
+  else get_state_kernel<2><<<blocks, threads, 0, s>>>(h->d, h->n, d_state);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_set_state(SoloHandle* h, const float* d_state, void* stream) {
+  if (!h || !d_state) return fail(h, SOLO_E_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int threads = 128, blocks = (h->n * 4 + threads - 1) / threads;
+  if (h->njl == 3) set_state_kernel<3><<<blocks, threads, 0, s>>>(h->d, h->sc, h->n, h->D0, d_state);
+  else set_state_kernel<2><<<blocks, threads, 0, s>>>(h->d, h->sc, h->n, h->D0, d_state);
+  h->launches++;
+  h->was_reset = true;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_set_goals(SoloHandle* h, const float* d_goals, void* stream) {
+  if (!h || !d_goals) return fail(h, SOLO_E_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  set_goal_kernel<<<(h->n + 127) / 128, 128, 0, s>>>(h->d, h->n, d_goals);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_get_contacts(SoloHandle* h, float* d_out, void* stream) {
+  if (!h || !d_out) return fail(h, SOLO_E_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  contacts_kernel<<<(h->n * 4 + 127) / 128, 128, 0, s>>>(h->d, h->sc, h->n, d_out);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_forward_dynamics(SoloHandle* h, const float* d_state, const float* d_tau, float* d_qdd, void* stream) {
+  if (!h || !d_state || !d_tau || !d_qdd) return fail(h, SOLO_E_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int threads = 128, blocks = (h->n * 4 + threads - 1) / threads;
+  if (h->njl == 3) fd_kernel<3><<<blocks, threads, 0, s>>>(h->mc, h->sc, h->n, d_state, d_tau, d_qdd);
+  else fd_kernel<2><<<blocks, threads, 0, s>>>(h->mc, h->sc, h->n, d_state, d_tau, d_qdd);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_substep(SoloHandle* h, const float* d_tau, void* stream) {
+  if (!h || !d_tau) return fail(h, SOLO_E_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  StepArgs a = make_step_args(h, MODE_SUBSTEP, h->n, d_tau, nullptr, nullptr, nullptr);
+  launch_step(h, a, s);
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_action_to_torque(SoloHandle* h, const float* d_actions, float* d_tau, void* stream) {
+  if (!h || !d_actions || !d_tau) return fail(h, SOLO_E_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int threads = 128, blocks = (h->n * 4 + threads - 1) / threads;
+  if (h->njl == 3) torque_kernel<3><<<blocks, threads, 0, s>>>(h->d, h->sc, h->n, h->A, d_actions, d_tau);
+  else torque_kernel<2><<<blocks, threads, 0, s>>>(h->d, h->sc, h->n, h->A, d_actions, d_tau);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_episode_stats(SoloHandle* h, SoloEpisodeStats* d_stats, void* stream) {
+  if (!h || !d_stats) return fail(h, SOLO_E_ARG, "null argument");
+  CUDA_TRY(h, cudaMemcpyAsync(d_stats, h->d.stats, (size_t)h->n * sizeof(SoloEpisodeStats),
+                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return SOLO_OK;
+}
+
+int solo_set_goal_radius(SoloHandle* h, double goal_radius) {
+  if (!h) return fail(nullptr, SOLO_E_ARG, "null handle");
+  h->goal_radius = (float)goal_radius;
+  return SOLO_OK;
+}
+
+int solo_gae(const float* d_rewards, const float* d_values, const float* d_masks, float* d_returns, int32_t T,
+             int32_t N, float gamma, float lam, int32_t use_gae, void* stream) {
+  if (!d_rewards || !d_values || !d_masks || !d_returns || T <= 0 || N <= 0)
+    return fail(nullptr, SOLO_E_ARG, "bad argument to solo_gae");
+  gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_rewards, d_values, d_masks, d_returns, T, N,
+                                                               gamma, lam, use_gae);
+  if (cudaGetLastError() != cudaSuccess) return fail(nullptr, SOLO_E_CUDA, "gae_kernel launch failed");
+  return SOLO_OK;
+}
+
+int64_t solo_launch_count(const SoloHandle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"
