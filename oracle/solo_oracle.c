@@ -944,7 +944,10 @@ static void clear_episode(OracleEnv* e) { /* baseEnv.py:72-77 */
 
 void oracle_set_state(OracleEnv* e, const double* s) {
   for (int k = 0; k < 3; k++) { e->pos[k] = s[k]; e->vlin[k] = s[7 + k]; e->vang[k] = s[10 + k]; }
-  for (int k = 0; k < 4; k++) e->quat[k] = s[3 + k];
+  {
+    double nn = sqrt(s[3] * s[3] + s[4] * s[4] + s[5] * s[5] + s[6] * s[6]);
+    for (int k = 0; k < 4; k++) e->quat[k] = s[3 + k] / nn;   /* orientation is a unit quaternion */
+  }
   for (int i = 0; i < e->m.num_links; i++) { e->q[i] = 0; e->qd[i] = 0; }
   for (int j = 0; j < e->nj; j++) { e->q[e->link_of_dof[j]] = s[13 + j]; e->qd[e->link_of_dof[j]] = s[13 + e->nj + j]; }
   for (int f = 0; f < SOLO_MAX_FEET; f++) { e->c_has[f] = 0; e->c_force[f] = 0; }

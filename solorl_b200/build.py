@@ -11,6 +11,8 @@ _SRC = os.path.join(_PKG, "csrc", "solo_kernels.cu")
 _DEPS = [_SRC] + [os.path.join(_PKG, "csrc", f) for f in ("solo_core.cuh", "solo_env.cuh", "solo_host_model.h")] + [
     os.path.join(os.path.dirname(_PKG), "include", "solo_b200.h")]
 LIB = os.path.join(_PKG, "libsolo_b200.so")
+_BENCH_SRC = os.path.join(_PKG, "csrc", "bench_util.cu")
+BENCH_LIB = os.path.join(_PKG, "libsolo_benchutil.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -25,6 +27,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         env.pop("CC", None)
         env.pop("CXX", None)
         subprocess.check_call(cmd, env=env)
+    if force or (not os.path.exists(BENCH_LIB)) or os.path.getmtime(_BENCH_SRC) > os.path.getmtime(BENCH_LIB):
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        env = dict(os.environ)
+        env.pop("CC", None)
+        env.pop("CXX", None)
+        subprocess.check_call([nvcc] + NVCC_FLAGS + ["-o", BENCH_LIB, _BENCH_SRC], env=env)
     return LIB
 
 

@@ -130,6 +130,11 @@ SOLO_HD void quat_to_rot(const float* q, float* R) { /* (x,y,z,w), base -> world
   R[6] = 2.f * (x * z - w * y);       R[7] = 2.f * (y * z + w * x);       R[8] = 1.f - 2.f * (x * x + y * y);
 }
 
+SOLO_HD void normalize_quat(float* q) {
+  float inv = 1.0f / sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+
 /* Symmetric 6x6 spatial inertia in (angular, linear) block form:
  *   f_ang = A w + H v ,  f_lin = H^T w + M v ;  A, M symmetric (6 floats), H full (9). */
 struct Sym6 {

@@ -555,6 +555,7 @@ __global__ void set_state_kernel(DevArrays d, SimConst sc, int n, int D0, const 
   load_base(d.base, e, st, goal, potential);
   for (int i = 0; i < 3; i++) { st.p[i] = s[i]; st.v[i] = s[7 + i]; st.w[i] = s[10 + i]; }
   for (int i = 0; i < 4; i++) st.q[i] = s[3 + i];
+  normalize_quat(st.q);
   Lane<NJL> ln;
 #pragma unroll
   for (int k = 0; k < NJL; k++) { ln.q[k] = s[13 + leg * NJL + k]; ln.qd[k] = s[13 + nj + leg * NJL + k]; }
@@ -614,6 +615,7 @@ __global__ void fd_kernel(ModelConst mc, SimConst sc, int n, const float* state,
   BaseState st;
   for (int i = 0; i < 3; i++) { st.p[i] = s[i]; st.v[i] = s[7 + i]; st.w[i] = s[10 + i]; }
   for (int i = 0; i < 4; i++) st.q[i] = s[3 + i];
+  normalize_quat(st.q);
   Lane<NJL> ln;
   float tau[NJL];
 #pragma unroll

@@ -201,6 +201,7 @@ void emu_set_state(void* h, const float* s) {
   Emu* e = (Emu*)h;
   for (int k = 0; k < 3; k++) { e->st.p[k] = s[k]; e->st.v[k] = s[7 + k]; e->st.w[k] = s[10 + k]; }
   for (int k = 0; k < 4; k++) e->st.q[k] = s[3 + k];
+  normalize_quat(e->st.q);
   for (int j = 0; j < e->nj; j++) { e->q[j] = s[13 + j]; e->qd[j] = s[13 + e->nj + j]; }
   for (int l = 0; l < 4; l++) e->cforce[l] = -1.f;
   for (int hh = 0; hh < e->sc.H; hh++) emu_cur_state(e, e->hist[hh]);

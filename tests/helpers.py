@@ -1,0 +1,72 @@
+"""Shared helpers of the test-suite."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+# ---- shared helpers -----------------------------------------------------------------------
+def make_config(robot="solo12", task="stand", control="torque", H=1, episode_length=400, **kw):
+    cfg = {"model_urdf": robot, "mode": "headless", "episode_length": episode_length, "frame_skip": 4,
+           "control": control, "task": task, "num_history_stack": H, "flat_ground": True}
+    if control in ("pd", "fpd", "fixed_pd"):
+        cfg["gains"] = [5., .2]     # configs/basic_pd.yaml:6
+    cfg.update(kw)
+    return cfg
+
+
+def random_states(rng, n, nj, vel_scale=1.0):
+    """Free-flight states: z ~ 1 m, random attitude, random velocities."""
+    s = np.zeros((n, 13 + 2 * nj))
+    s[:, :3] = rng.normal(size=(n, 3)) * 0.3
+    s[:, 2] += 1.0
+    q = rng.normal(size=(n, 4))
+    s[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    s[:, 7:10] = rng.normal(size=(n, 3)) * vel_scale
+    s[:, 10:13] = rng.normal(size=(n, 3)) * 2 * vel_scale
+    s[:, 13:13 + nj] = rng.uniform(-2, 2, size=(n, nj))
+    s[:, 13 + nj:] = rng.normal(size=(n, nj)) * 5 * vel_scale
+    return s.astype(np.float32).astype(np.float64)   # exactly representable in fp32
+
+
+def stance_states(rng, n, nj, z=0.24, noise=0.1):
+    """Bent-leg stance near the SRDF nominal posture (srdf/solo.srdf:69-83: z 0.235, HFE +-0.8,
+    KFE -+1.6): feet on or near the ground, well-conditioned contact problem."""
+    s = np.zeros((n, 13 + 2 * nj))
+    s[:, 2] = z + rng.normal(size=n) * 0.005
+    s[:, 6] = 1.0
+    njl = nj // 4
+    for l in range(4):
+        sg = 1.0 if l < 2 else -1.0
+        if njl == 3:
+            s[:, 13 + l * 3] = rng.normal(size=n) * noise * 0.5
+        s[:, 13 + l * njl + njl - 2] = 0.8 * sg + rng.normal(size=n) * noise
+        s[:, 13 + l * njl + njl - 1] = -1.6 * sg + rng.normal(size=n) * noise
+    s[:, 7:10] = rng.normal(size=(n, 3)) * 0.1
+    s[:, 13 + nj:] = rng.normal(size=(n, nj)) * 0.5
+    return s.astype(np.float32).astype(np.float64)
+
+
+def euler_slots(d0, blocks):
+    idx = []
+    for b in range(blocks):
+        idx += [b * d0 + 1, b * d0 + 2, b * d0 + 3]
+    return np.array(idx)
+
+
+def obs_diff(a, b, d0):
+    """|a - b| with the three Euler slots of every D0 block compared modulo 1: the reference's
+    observation maps an Euler angle e to (e mod 2)/2 (solo.py:206), which jumps by 1
+    at e = 0, so two implementations that agree to 1e-9 on e can differ by ~1 in that slot."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    d = np.abs(a - b)
+    blocks = a.shape[-1] // d0
+    sl = euler_slots(d0, blocks)
+    w = d[..., sl]
+    w = np.minimum(w, np.abs(1.0 - w))
+    w = np.minimum(w, np.abs(2.0 - d[..., sl]))
+    d[..., sl] = w
+    return d

