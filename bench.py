@@ -36,14 +36,17 @@ CONFIG = {"model_urdf": "solo12", "mode": "headless", "episode_length": 400, "fr
 WORKLOAD = "configs/basic12.yaml-shaped: Solo12 walk, torque control, H=1, frame_skip 4, random actions"
 
 
-def algorithmic_flops_per_env_step(nj, nc, iters=50, frame_skip=4):
-    """F_step = S (F_ABA + F_setup + F_PGS + F_int) + 400, m = 3 nc rows."""
-    nb, ndof, m = nj + 1, nj + 6, 3.0 * nc
+def algorithmic_flops_per_env_step(nj, nc_sum, sweep_feet, frame_skip=4):
+    """F_step = S (F_ABA + F_int) + sum_substeps (F_setup + F_PGS) + 400 with m = 3 nc
+    rows per substep.  nc_sum = sum over the S substeps of feet in contact; sweep_feet = sum over
+    substeps of feet in contact x PGS sweeps actually run (K = 50 only when the residual test never
+    fires), both measured by the kernel (solo_get_work_counters)."""
+    nb, ndof = nj + 1, nj + 6
     f_aba = 429 * nb - 502
-    f_setup = m * (250 * nb + 2 * ndof)
-    f_pgs = iters * m * (4 * ndof + 10)
+    f_setup = 3.0 * nc_sum * (250 * nb + 2 * ndof)
+    f_pgs = 3.0 * sweep_feet * (4 * ndof + 10)
     f_int = 80 * nb
-    return frame_skip * (f_aba + f_setup + f_pgs + f_int) + 400
+    return frame_skip * (f_aba + f_int) + f_setup + f_pgs + 400
 
 
 def algorithmic_bytes_per_env_step(nj, D):
@@ -199,11 +202,17 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    contacts, resets = [], []
+    ncs, sweeps, resets = [], [], []
+
+    def sample_work(d):
+        w = sim.get_work_counters().float().mean(0)
+        ncs.append(w[0].item())
+        sweeps.append(w[1].item())
+        resets.append(d.mean().item())
+
     for i in range(max(args.warmup, 3)):
         _, _, d, _ = env.step(acts[i % nact])
-        contacts.append(sim.get_contacts()[:, :, 1].sum(1).mean().item())
-        resets.append(d.mean().item())
+        sample_work(d)
 
     # ---- device-resident timing: exactly K steps, L2 flushed between timed steps -------------
     sampler = ClockSampler(local)
@@ -223,10 +232,9 @@ def run_ours(args):
     clocks = sampler.stop()
     step_ms = np.array([a.elapsed_time(b) for a, b in evs])
     total_ms = float(step_ms.sum())
-    for i in range(8):
+    for i in range(16):
         _, _, d, _ = env.step(acts[i % nact])
-        contacts.append(sim.get_contacts()[:, :, 1].sum(1).mean().item())
-        resets.append(d.mean().item())
+        sample_work(d)
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -269,8 +277,8 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel (step_kernel: one launch per step) ----------------------
-    nc = float(np.mean(contacts))
-    flops = algorithmic_flops_per_env_step(nj, nc) * n
+    nc_sum, sweep_feet = float(np.mean(ncs)), float(np.mean(sweeps))
+    flops = algorithmic_flops_per_env_step(nj, nc_sum, sweep_feet) * n
     kernel_ms = total_ms / args.steps if world == 1 else float(step_ms.mean())
     fma_tflops = C.c_double()
     fma_ms = C.c_double()
@@ -292,7 +300,9 @@ def run_ours(args):
         "frac": achieved / peak, "traffic": None,
         "peak_source": "FP32 FMA microbenchmark measured live in this run (solo_bench_fma_peak)" if rc == 0
         else "fallback 148 SM x 128 lanes x 2 x 1.965 GHz",
-        "algorithmic_flops_per_env_step": algorithmic_flops_per_env_step(nj, nc), "mean_contacts": nc,
+        "algorithmic_flops_per_env_step": algorithmic_flops_per_env_step(nj, nc_sum, sweep_feet),
+        "mean_contacts_per_substep": nc_sum / 4.0,
+        "mean_pgs_sweeps_per_contact_substep": (sweep_feet / nc_sum) if nc_sum > 0 else 0.0,
         "resets_per_env_step": float(np.mean(resets)), "kernel_ms": kernel_ms,
         "hbm": {"bound": "hbm", "achieved": abytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": abytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
@@ -304,7 +314,8 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n, "robot": "solo12", "task": "walk", "control": "torque",
-                   "num_history_stack": 1, "episode_length": 400, "solver_iters": 50, "reset_mode": "cached",
+                   "num_history_stack": 1, "episode_length": 400, "solver_iters": 50,
+                   "solver_residual_threshold": 1e-7, "reset_mode": "cached",
                    "l2": "flushed (256 MiB write) between timed steps; per-step CUDA events summed",
                    "parallelism": f"env-shard x{world}"},
         "clocks": clocks, "gpu_launches": int(launches),

@@ -108,7 +108,10 @@ typedef struct SoloSimParams {
   double lin_damping;        /* 0.04  Bullet btMultiBody linear damping  */
   double ang_damping;        /* 0.04  Bullet btMultiBody angular damping */
   double max_coord_vel;      /* 100   Bullet m_maxCoordinateVelocity */
-  int32_t solver_iters;      /* 50    PyBullet numSolverIterations */
+  int32_t solver_iters;      /* 50    PyBullet numSolverIterations (iteration cap) */
+  double solver_residual_threshold; /* 1e-7  PyBullet solverResidualThreshold: the sweep loop stops once
+                                     * the largest squared row velocity residual of an iteration is <= this;
+                                     * 0 = always run solver_iters iterations */
   double contact_erp;        /* 0.2   contact error-reduction parameter */
   double contact_slop;       /* 1e-5  linear slop added to the contact distance */
   double contact_margin;     /* 0.02  contact point exists while distance < margin */
@@ -202,6 +205,11 @@ int solo_set_goals(SoloHandle* h, const float* d_goals, void* stream);
 /* Contact record of the last substep: per env, per foot: flag (0/1 as in
  * solo.py:310-323), has_point, normal force [N]. d_out float[N, 4, 3]. */
 int solo_get_contacts(SoloHandle* h, float* d_out, void* stream);
+
+/* Measurement hook: work done by the last env step, per env: d_out int32[N,2] =
+ * (sum over substeps of feet in contact, sum over substeps of feet-in-contact x PGS sweeps run).
+ * bench.py turns these into the algorithmic FLOPs of the launch. */
+int solo_get_work_counters(SoloHandle* h, int32_t* d_out, void* stream);
 
 /* Contact-free forward dynamics on given states: qdd [N, 6+nj] =
  * (base angular acc (world), base linear acc (world), joint acc) for joint torques

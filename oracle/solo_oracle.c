@@ -203,6 +203,7 @@ struct OracleEnv {
   /* rng */
   uint64_t seed; int64_t env_id; uint32_t episode, draw;
   int settle_last;
+  int last_iters;        /* PGS iterations used by the last substep with contacts */
 };
 
 /* per-step workspace of the articulated-body algorithm, Bullet-style: every spatial
@@ -230,6 +231,7 @@ void oracle_default_params(SoloSimParams* p) {
   p->ang_damping = 0.04;          /* [3P] */
   p->max_coord_vel = 100.0;       /* [3P] m_maxCoordinateVelocity */
   p->solver_iters = 50;           /* [3P] PyBullet numSolverIterations */
+  p->solver_residual_threshold = 1e-7; /* [3P] PyBullet solverResidualThreshold */
   p->contact_erp = 0.2;           /* [3P] */
   p->contact_slop = 1e-5;         /* [3P] */
   p->contact_margin = 0.02;       /* [3P] contact breaking threshold */
@@ -282,6 +284,7 @@ int oracle_act_dim(const OracleEnv* e) { return e->act_dim; }
 int oracle_obs_dim0(const OracleEnv* e) { return e->d0; }
 int oracle_obs_dim(const OracleEnv* e) { return e->d; }
 int oracle_settle_count_last(const OracleEnv* e) { return e->settle_last; }
+int oracle_last_solver_iters(const OracleEnv* e) { return e->last_iters; }
 
 static void env_rng(OracleEnv* e, uint32_t w[4]) {
   w[0] = (uint32_t)((uint64_t)e->env_id & 0xffffffffu);
@@ -647,14 +650,21 @@ void oracle_substep(OracleEnv* e, const double* tau) {
         row->lambda = 0; /* [3P] warm starting is disabled for multibody contacts */
       }
     }
-    /* 4 PGS */
+    /* 4 PGS ([3P] btMultiBodyConstraintSolver::solveSingleIteration; the loop of
+     * solveGroupCacheFriendlyIterations stops after the iteration whose largest squared row
+     * residual, in velocity units deltaImpulse / jacDiagABInv, is <= the threshold) */
+    e->last_iters = 0;
     for (int it = 0; it < p->solver_iters; it++) {
+      double res2 = 0;
+      e->last_iters = it + 1;
       for (int c = 0; c < nc; c++) {
         Row* r = &rn[c];
         double delta = r->rhs - rowdot(nd, r->J, dv) * r->dinv;
         double sum = r->lambda + delta;
         if (sum < 0) { delta = -r->lambda; r->lambda = 0; } else r->lambda = sum;
         for (int k = 0; k < nd; k++) dv[k] += r->u[k] * delta;
+        double rv = delta / r->dinv;
+        if (rv * rv > res2) res2 = rv * rv;
       }
       for (int c = 0; c < nc; c++) {
         double lim = p->friction * rn[c].lambda;
@@ -671,6 +681,8 @@ void oracle_substep(OracleEnv* e, const double* tau) {
           dA = sumA - a->lambda; a->lambda = sumA;
           dB = sumB - b->lambda; b->lambda = sumB;
           for (int k = 0; k < nd; k++) dv[k] += a->u[k] * dA + b->u[k] * dB;
+          double rv = dA / a->dinv + dB / b->dinv;
+          if (rv * rv > res2) res2 = rv * rv;
         } else {
           for (int s = 0; s < 2; s++) {
             Row* r = s ? b : a;
@@ -678,9 +690,12 @@ void oracle_substep(OracleEnv* e, const double* tau) {
             double sum = clampd(r->lambda + delta, -lim, lim);
             delta = sum - r->lambda; r->lambda = sum;
             for (int k = 0; k < nd; k++) dv[k] += r->u[k] * delta;
+            double rv = delta / r->dinv;
+            if (rv * rv > res2) res2 = rv * rv;
           }
         }
       }
+      if (res2 <= p->solver_residual_threshold) break;
     }
     /* 5 apply */
     for (int k = 0; k < 3; k++) { e->vang[k] += dv[k]; e->vlin[k] += dv[3 + k]; }

@@ -19,7 +19,7 @@ _lib = None
 SYMBOLS = [
     "solo_default_params", "solo_dims", "solo_create", "solo_destroy", "solo_last_error",
     "solo_reset", "solo_step", "solo_step_host", "solo_get_observation", "solo_get_state",
-    "solo_set_state", "solo_set_goals", "solo_get_contacts", "solo_forward_dynamics",
+    "solo_set_state", "solo_set_goals", "solo_get_contacts", "solo_get_work_counters", "solo_forward_dynamics",
     "solo_substep", "solo_action_to_torque", "solo_episode_stats", "solo_set_goal_radius",
     "solo_gae", "solo_launch_count",
 ]
@@ -57,6 +57,7 @@ def lib():
     L.solo_set_state.argtypes = [vp, fp, vp]
     L.solo_set_goals.argtypes = [vp, fp, vp]
     L.solo_get_contacts.argtypes = [vp, fp, vp]
+    L.solo_get_work_counters.argtypes = [vp, fp, vp]
     L.solo_forward_dynamics.argtypes = [vp, fp, fp, fp, vp]
     L.solo_substep.argtypes = [vp, fp, vp]
     L.solo_action_to_torque.argtypes = [vp, fp, fp, vp]

@@ -57,6 +57,7 @@ class SoloSimParams(C.Structure):
         ("ang_damping", C.c_double),
         ("max_coord_vel", C.c_double),
         ("solver_iters", C.c_int32),
+        ("solver_residual_threshold", C.c_double),
         ("contact_erp", C.c_double),
         ("contact_slop", C.c_double),
         ("contact_margin", C.c_double),
@@ -156,6 +157,7 @@ def default_params() -> SoloSimParams:
     p.ang_damping = 0.04
     p.max_coord_vel = 100.0
     p.solver_iters = 50
+    p.solver_residual_threshold = 1e-7
     p.contact_erp = 0.2
     p.contact_slop = 1e-5
     p.contact_margin = 0.02
@@ -191,7 +193,7 @@ def params_from_config(config: dict, model: Optional[SoloModel] = None) -> SoloS
     ``episode_length`` (required), ``frame_skip`` 4, ``control`` 'torque', ``task``
     'stand', ``gains`` None, ``num_history_stack`` 0, ``flat_ground`` True,
     ``use_treadmill`` False.  Extra keys (all default to the reference-faithful value):
-    ``torque_hold``, ``solver_iters``, ``contact_erp``, ``reset_mode``.
+    ``torque_hold``, ``solver_iters``, ``solver_residual_threshold``, ``contact_erp``, ``reset_mode``.
     """
     p = default_params()
     p.episode_length = int(config["episode_length"])           # baseEnv.py:164 (required)
@@ -222,7 +224,7 @@ def params_from_config(config: dict, model: Optional[SoloModel] = None) -> SoloS
         if k in config:
             setattr(p, k, int(config[k]))
     for k in ("contact_erp", "contact_margin", "contact_slop", "friction", "lin_damping",
-              "ang_damping", "goal_radius"):
+              "ang_damping", "goal_radius", "solver_residual_threshold"):
         if k in config:
             setattr(p, k, float(config[k]))
     rm = config.get("reset_mode", "cached")

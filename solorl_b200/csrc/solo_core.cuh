@@ -10,8 +10,10 @@
  * of the fp64 oracle: the joint-axis inertia D = a.A.a is a sum of positive terms
  * instead of the difference of large m|r|^2 terms it would be about the base origin.
  * The four legs are summed into the floating base with two xor-shuffles and the 6x6 base
- * solve is done redundantly by the four lanes.  Contacts are solved in Delassus form A = P^T IA0^-1 P + blockdiag(L)
- * by one thread per environment (see pgs_solve).
+ * solve is done redundantly by the four lanes.  Contacts are solved in Delassus form
+ * A = P^T IA0^-1 P + blockdiag(L): each lane keeps the three rows of its own foot in
+ * registers and the projected Gauss-Seidel sweep broadcasts one impulse change per row
+ * relaxation with a group-masked shuffle (see PgsLane).
  *
  * This formulation is deliberately different from the CPU oracle (oracle/solo_oracle.c:
  * link-COM frames, 6x6 transforms, one impulse-response pass per contact row), which is
@@ -64,6 +66,7 @@ struct ModelConst {
 struct SimConst {
   float dt, inv_dt, gz, klin, kang, vmax, erp, slop, margin, mu;
   int iters, cone, frame_skip, torque_hold;
+  float res_thr;   /* squared velocity residual below which the PGS sweep loop stops (0 = never) */
   int control;
   float kp, kd, max_torque, q_limit, qd_limit;
   int task, episode_length, H;
@@ -573,10 +576,8 @@ SOLO_HD void contact_setup(const LegConst& lc, const ModelConst& mc, const SimCo
 SOLO_HD constexpr int row_of(int foot, int m) { return m == 0 ? foot : 4 + 2 * foot + (m - 1); }
 
 /* Rows of the scaled Delassus matrix owned by one foot, built one column block at a time:
- *   A = P^T IA0^-1 P + blockdiag(L),  B[r][c] = A[r][c] / A[r][r],  g0[r] = b[r] / A[r][r].
- * assemble_block adds the 3x3 block against foot j (Kj = K of foot j, fetched from that
- * lane); assemble_finish adds the leg-local block, scales and stores.  Inactive feet
- * produce zero rows/columns.  Stored at Bout[(r*kRows + c)*stride], g0out[r*stride]. */
+ *   A = P^T IA0^-1 P + blockdiag(L),  B[m][c] = A[r_m][c] / A[r_m][r_m],  g0[m] = b[m] / A[r_m][r_m].
+ * assemble_block adds the 3x3 block against foot j (Kj = K of foot j, fetched from that lane). */
 template <int NJL>
 SOLO_HD void assemble_block(const Lane<NJL>& ln, int j, const float Kj[3][6], float rows[3][kRows]) {
 #pragma unroll
@@ -585,95 +586,78 @@ SOLO_HD void assemble_block(const Lane<NJL>& ln, int j, const float Kj[3][6], fl
     for (int n = 0; n < 3; n++) rows[m][row_of(j, n)] = dot6(ln.P[m], Kj[n]);
   }
 }
+
+/* Projected Gauss-Seidel state of one foot (= one lane): its three rows of B, and for those
+ * rows  g[m] = lambda[m] + (rhs[m] - sum_c A[m][c] lambda[c]) / A[m][m],  the value the row would
+ * take if relaxed now.  Relaxing row r anywhere changes g[m] by -B[m][r] * dlambda_r, so a sweep is:
+ * owner clamps its g, the impulse change is broadcast to the env's four lanes, every lane applies
+ * three FMAs.  Sweep order and projections restate btMultiBodyConstraintSolver::solveSingleIteration
+ * [3P]: all normal rows (lambda >= 0), then per contact the friction pair, both candidates taken from
+ * the same state and projected radially onto the circle of radius mu*lambda_n
+ * (resolveConeFrictionConstraintRows; its atan2/sin/cos == the x/|x| scaling used here), or row by
+ * row onto [-mu lambda_n, mu lambda_n] when cone friction is off.  No warm start.  The sweep loop
+ * ends after solver_iters iterations or once the largest squared velocity residual
+ * (dlambda * A[r][r])^2 of an iteration is <= solver_residual_threshold. */
+struct PgsLane {
+  float B[3][kRows];
+  float g[3], lam[3], diag[3];
+};
 template <int NJL>
-SOLO_HD void assemble_finish(const Lane<NJL>& ln, int foot, float rows[3][kRows],
-                             unsigned active_mask, float* Bout, float* g0out, int stride) {
+SOLO_HD void pgs_lane_init(const Lane<NJL>& ln, int foot, float rows[3][kRows], unsigned active_mask,
+                           PgsLane& pl) {
   const int lidx[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
 #pragma unroll
   for (int m = 0; m < 3; m++) {
     const int r = row_of(foot, m);
 #pragma unroll
     for (int n = 0; n < 3; n++) rows[m][row_of(foot, n)] += ln.Lm[lidx[m][n]];
-    float invd = ln.active ? 1.0f / rows[m][r] : 0.f;
+    const float d = rows[m][r];
+    const float invd = ln.active ? 1.0f / d : 0.f;
+    pl.diag[m] = ln.active ? d : 0.f;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
 #pragma unroll
       for (int n = 0; n < 3; n++) {
         const int c = row_of(j, n);
-        float v = (((active_mask >> j) & 1u) && c != r) ? rows[m][c] * invd : 0.f;
-        Bout[(r * kRows + c) * stride] = v;
+        pl.B[m][c] = (((active_mask >> j) & 1u) && c != r) ? rows[m][c] * invd : 0.f;
       }
     }
-    g0out[r * stride] = ln.b[m] * invd;
+    pl.g[m] = ln.b[m] * invd;
+    pl.lam[m] = 0.f;
   }
 }
-
-/* Projected Gauss-Seidel on the scaled Delassus system, one thread per environment.
- * State g[r] = lambda[r] + (rhs[r] - sum_c A[r][c] lambda[c]) / A[r][r] is the value row r
- * would take if relaxed now, so relaxing a row is clamp + 11 independent FMAs.
- * Sweep order and projections restate btMultiBodyConstraintSolver::solveSingleIteration:
- * all normal rows (lambda >= 0), then per contact the friction pair, both candidates taken
- * from the same state and projected radially onto the circle of radius mu*lambda_n
- * (resolveConeFrictionConstraintRows; atan2/sin/cos there == x/|x| scaling here), or row by
- * row onto [-mu lambda_n, mu lambda_n] when cone friction is off.  No warm start, fixed
- * iteration count. */
-SOLO_HD void pgs_solve(const float* B, const float* g0, int stride, int iters, int cone, float mu,
-                       unsigned feet_mask, float* lam_out) {
-  float Bm[kRows][kRows], g[kRows], lam[kRows];
+/* candidate for this lane's normal row: new value, impulse change, velocity residual */
+SOLO_HD void pgs_normal_candidate(const PgsLane& pl, float& nv, float& d, float& rv) {
+  nv = fmaxf(pl.g[0], 0.f);
+  d = nv - pl.lam[0];
+  rv = d * pl.diag[0];
+}
+/* candidates for this lane's friction pair (cone) */
+SOLO_HD void pgs_cone_candidate(const PgsLane& pl, float mu, float& nA, float& nB, float& dA, float& dB,
+                                float& rv) {
+  const float lim = mu * pl.lam[0];
+  const float sA = pl.g[1], sB = pl.g[2];
+  const float n2 = sA * sA + sB * sB;
+  const float inv = n2 > 0.f ? solo_rsqrt(n2) : 0.f;
+  const float limA = lim * fabsf(sA) * inv;
+  const float limB = n2 > 0.f ? lim * fabsf(sB) * inv : lim;
+  nA = clampf(sA, -limA, limA);
+  nB = clampf(sB, -limB, limB);
+  dA = nA - pl.lam[1];
+  dB = nB - pl.lam[2];
+  rv = dA * pl.diag[1] + dB * pl.diag[2];
+}
+/* candidate for one friction row (pyramid), q = 0/1 */
+SOLO_HD void pgs_pyramid_candidate(const PgsLane& pl, float mu, int q, float& nv, float& d, float& rv) {
+  const float lim = mu * pl.lam[0];
+  nv = clampf(pl.g[1 + q], -lim, lim);
+  d = nv - pl.lam[1 + q];
+  rv = d * pl.diag[1 + q];
+}
+/* apply the impulse change d of global row `col` to this lane's rows */
+SOLO_HD void pgs_apply(PgsLane& pl, int col, float d) {
 #pragma unroll
-  for (int r = 0; r < kRows; r++) {
-    g[r] = g0[r * stride];
-    lam[r] = 0.f;
-#pragma unroll
-    for (int c = 0; c < kRows; c++) Bm[r][c] = B[(r * kRows + c) * stride];
-  }
-  for (int it = 0; it < iters; it++) {
-#pragma unroll
-    for (int f = 0; f < 4; f++) {
-      if (!(feet_mask & (1u << f))) continue;
-      float nv = fmaxf(g[f], 0.f);
-      float d = nv - lam[f];
-      lam[f] = nv;
-#pragma unroll
-      for (int s = 0; s < kRows; s++)
-        if (s != f) g[s] -= Bm[s][f] * d;
-    }
-#pragma unroll
-    for (int f = 0; f < 4; f++) {
-      if (!(feet_mask & (1u << f))) continue;
-      const int a = 4 + 2 * f, b = 5 + 2 * f;
-      float lim = mu * lam[f];
-      if (cone) {
-        float sA = g[a], sB = g[b];
-        float n2 = sA * sA + sB * sB;
-        float inv = n2 > 0.f ? solo_rsqrt(n2) : 0.f;
-        float limA = lim * fabsf(sA) * inv;
-        float limB = n2 > 0.f ? lim * fabsf(sB) * inv : lim;
-        float nA = clampf(sA, -limA, limA), nB = clampf(sB, -limB, limB);
-        float dA = nA - lam[a], dB = nB - lam[b];
-        lam[a] = nA; lam[b] = nB;
-#pragma unroll
-        for (int s = 0; s < kRows; s++) {
-          if (s == a) g[s] -= Bm[s][b] * dB;
-          else if (s == b) g[s] -= Bm[s][a] * dA;
-          else g[s] -= Bm[s][a] * dA + Bm[s][b] * dB;
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          const int r = q ? b : a;
-          float nv = clampf(g[r], -lim, lim);
-          float d = nv - lam[r];
-          lam[r] = nv;
-#pragma unroll
-          for (int s = 0; s < kRows; s++)
-            if (s != r) g[s] -= Bm[s][r] * d;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < kRows; r++) lam_out[r * stride] = lam[r];
+  for (int m = 0; m < 3; m++) pl.g[m] -= pl.B[m][col] * d;
 }
 
 /* Wrench on the base produced by this foot's impulses, already multiplied by IA0^-1:

@@ -19,6 +19,9 @@ struct EnvBook {
   uint32_t draw;
   float reward_sum;      /* baseEnv.py:33 */
   float dr[5];           /* stand, joint_pose, torque, balance, progress (baseEnv.py:34-38) */
+  /* work done by the last env step (measurement only): sum over substeps of the number of feet
+   * in contact, and of (feet in contact x PGS sweeps executed) */
+  int32_t nc_sum, sweep_feet;
 };
 
 /* layout of the base record base[env][16] */

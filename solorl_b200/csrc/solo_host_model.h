@@ -96,7 +96,8 @@ inline int build_sim_const(const SoloSimParams& p, SimConst& sc, std::string& er
   memset(&sc, 0, sizeof(sc));
   if (p.abi_version != SOLO_ABI_VERSION) { err = "params ABI version mismatch"; return SOLO_E_ARG; }
   if (p.dt <= 0 || p.frame_skip <= 0 || p.solver_iters < 0 || p.episode_length <= 0 ||
-      p.num_history_stack < 0 || p.settle_max < p.settle_min || p.settle_min < 0) {
+      p.num_history_stack < 0 || p.settle_max < p.settle_min || p.settle_min < 0 ||
+      p.solver_residual_threshold < 0) {
     err = "bad simulation parameters"; return SOLO_E_ARG;
   }
   if (p.control < 0 || p.control > 2 || p.task < 0 || p.task > 2) { err = "bad control/task"; return SOLO_E_ARG; }
@@ -104,6 +105,7 @@ inline int build_sim_const(const SoloSimParams& p, SimConst& sc, std::string& er
   sc.klin = (float)p.lin_damping; sc.kang = (float)p.ang_damping; sc.vmax = (float)p.max_coord_vel;
   sc.erp = (float)p.contact_erp; sc.slop = (float)p.contact_slop; sc.margin = (float)p.contact_margin;
   sc.mu = (float)p.friction; sc.iters = p.solver_iters; sc.cone = p.cone_friction;
+  sc.res_thr = (float)p.solver_residual_threshold;
   sc.frame_skip = p.frame_skip; sc.torque_hold = p.torque_hold;
   sc.control = p.control; sc.kp = (float)p.kp; sc.kd = (float)p.kd;
   sc.max_torque = (float)p.max_torque; sc.q_limit = (float)p.joint_state_limit;
@@ -122,7 +124,7 @@ inline void fill_default_params(SoloSimParams* p) {
   p->abi_version = SOLO_ABI_VERSION;
   p->dt = 1.0 / 240.0; p->frame_skip = 4; p->gravity_z = -9.81;
   p->lin_damping = 0.04; p->ang_damping = 0.04; p->max_coord_vel = 100.0;
-  p->solver_iters = 50; p->contact_erp = 0.2; p->contact_slop = 1e-5; p->contact_margin = 0.02;
+  p->solver_iters = 50; p->solver_residual_threshold = 1e-7; p->contact_erp = 0.2; p->contact_slop = 1e-5; p->contact_margin = 0.02;
   p->friction = 1.0; p->cone_friction = 1; p->torque_hold = 0;
   p->control = SOLO_CONTROL_TORQUE; p->kp = 0; p->kd = 0; p->max_torque = 3.0;
   p->joint_state_limit = 10.0; p->joint_vel_limit = 100.0;

@@ -2,15 +2,15 @@
  * solo_kernels.cu — sm_100a kernels and the C-ABI (include/solo_b200.h) of the batched
  * Solo8/Solo12 env step.
  *
- * step_kernel: ONE launch per env step.  A block owns 32 environments:
- *   warps 0-3  "leg lanes": thread t = (env t/4, leg t%4); articulated-body dynamics,
- *              contact-row assembly, impulse application, integration, observation /
- *              reward / termination / auto-reset.  Cross-leg sums are xor-shuffles.
- *   warp  4    "solver lanes": thread = one env; fixed-iteration projected Gauss-Seidel on
- *              the 12x12 scaled Delassus system handed over through shared memory.
- * While one role works the other waits at a block barrier, so idle *warps* (free) replace
- * idle *lanes* (which would cost issue slots): the sequential PGS sweep runs with all 32
- * lanes busy instead of 1 in 4.
+ * step_kernel: ONE launch per env step.  Thread t of a warp = (env t/4, leg t%4): four lanes
+ * per environment, eight environments per warp, one warp per block (at 4096 envs that is 512
+ * warps for the 592 warp schedulers of a B200, i.e. one warp per scheduler: the step is a pure
+ * dependent-latency problem, so the design minimises the per-warp instruction chain rather than
+ * occupancy).  All cross-leg traffic — the sum of the four legs' articulated inertias into the
+ * floating base, the exchange of IA0^-1 P blocks for the Delassus rows, and the one-value
+ * broadcast per projected-Gauss-Seidel row relaxation — is register shuffles restricted to the
+ * env's 4-lane group, so a group never waits for another env; there is no block barrier and no
+ * shared-memory staging in the step (shared memory only holds the per-leg model constants).
  *
  * HBM layout (structure of arrays, fp32):
  *   base  [cap][16]  : pos3 quat4 linvel3 angvel3 goal2 potential1   (4 x float4 per env)
@@ -32,9 +32,8 @@
 
 namespace solo {
 
-constexpr int kEnvsPerBlock = 32;
-constexpr int kLegThreads = 128;
-constexpr int kBlockThreads = 160;
+constexpr int kEnvsPerBlock = 8;
+constexpr int kBlockThreads = 32;
 
 enum { MODE_STEP = 0, MODE_SETTLE = 1, MODE_SUBSTEP = 2 };
 
@@ -85,25 +84,22 @@ struct ResetArgs {
 };
 
 struct Smem {
-  float B[kRows * kRows][kEnvsPerBlock];
-  float g0[kRows][kEnvsPerBlock];
-  float lam[kRows][kEnvsPerBlock];
-  unsigned mask[kEnvsPerBlock];
   LegConst leg[4];
 };
 
-__device__ __forceinline__ float sum4(float x) {
-  x += __shfl_xor_sync(0xffffffffu, x, 1);
-  x += __shfl_xor_sync(0xffffffffu, x, 2);
+/* sum over the four lanes of an env (xor butterfly inside the 4-lane group `gm`) */
+__device__ __forceinline__ float sum4(unsigned gm, float x) {
+  x += __shfl_xor_sync(gm, x, 1);
+  x += __shfl_xor_sync(gm, x, 2);
   return x;
 }
-__device__ __forceinline__ void sum4_sym6(Sym6& I) {
+__device__ __forceinline__ void sum4_sym6(unsigned gm, Sym6& I) {
 #pragma unroll
-  for (int i = 0; i < 6; i++) I.A[i] = sum4(I.A[i]);
+  for (int i = 0; i < 6; i++) I.A[i] = sum4(gm, I.A[i]);
 #pragma unroll
-  for (int i = 0; i < 9; i++) I.H[i] = sum4(I.H[i]);
+  for (int i = 0; i < 9; i++) I.H[i] = sum4(gm, I.H[i]);
 #pragma unroll
-  for (int i = 0; i < 6; i++) I.M[i] = sum4(I.M[i]);
+  for (int i = 0; i < 6; i++) I.M[i] = sum4(gm, I.M[i]);
 }
 
 /* ---- the pieces of one D0-row of the observation that a lane produces -------------- */
@@ -262,17 +258,20 @@ __device__ __forceinline__ void begin_reset(const DevArrays& d, const SimConst& 
 
 /* One Bullet-equivalent substep for the four lanes of an env (see solo_core.cuh). */
 template <int NJL>
-__device__ __forceinline__ void group_substep(Smem& sm, const ModelConst& mc, const SimConst& sc, int el, int leg,
-                                              BaseState& st, Lane<NJL>& ln, const float* tau, float& cforce) {
-  const LegConst& lc = sm.leg[leg];
+__device__ __forceinline__ void group_substep(const LegConst& lc, const ModelConst& mc, const SimConst& sc,
+                                              int leg, BaseState& st, Lane<NJL>& ln, const float* tau, float& cforce,
+                                              int& nc_sum, int& sweep_feet) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned gbase = lane & ~3u;
+  const unsigned gm = 0xFu << gbase;
   BaseWork bw;
   base_prepare(st, bw);
   Sym6 IA;
   float pA[6], a0[6];
   leg_inward<NJL>(lc, sc, bw, ln, tau, IA, pA);
-  sum4_sym6(IA);
+  sum4_sym6(gm, IA);
 #pragma unroll
-  for (int i = 0; i < 6; i++) pA[i] = sum4(pA[i]);
+  for (int i = 0; i < 6; i++) pA[i] = sum4(gm, pA[i]);
   base_solve(mc, sc, bw, IA, pA, a0);
   {
     float qdd[NJL], aw[3], al[3];
@@ -283,38 +282,76 @@ __device__ __forceinline__ void group_substep(Smem& sm, const ModelConst& mc, co
     for (int k = 0; k < NJL; k++) ln.qd[k] = clampf(ln.qd[k] + sc.dt * qdd[k], -sc.vmax, sc.vmax);
   }
   contact_setup<NJL>(lc, mc, sc, st, bw, ln);
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned gbase = lane & ~3u;
   unsigned amask = 0;
 #pragma unroll
-  for (int j = 0; j < 4; j++) amask |= (unsigned)(__shfl_sync(0xffffffffu, ln.active, gbase + j) != 0) << j;
-  if (__any_sync(0xffffffffu, amask != 0)) {
-    float rows[3][kRows];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      float Kj[3][6];
-#pragma unroll
-      for (int n = 0; n < 3; n++) {
-#pragma unroll
-        for (int i = 0; i < 6; i++) Kj[n][i] = __shfl_sync(0xffffffffu, ln.K[n][i], gbase + j);
-      }
-      assemble_block<NJL>(ln, j, Kj, rows);
-    }
-    assemble_finish<NJL>(ln, leg, rows, amask, &sm.B[0][el], &sm.g0[0][el], kEnvsPerBlock);
-  }
-  if (leg == 0) sm.mask[el] = amask;
-  const int any = __syncthreads_or(amask != 0);
+  for (int j = 0; j < 4; j++) amask |= (unsigned)(__shfl_sync(gm, ln.active, gbase + j) != 0) << j;
   float lam3[3] = {0.f, 0.f, 0.f};
-  if (any) {
-    __syncthreads();   /* solver warp runs pgs_solve between the two barriers */
+  if (amask) {   /* uniform over the env's four lanes */
+    PgsLane pl;
+    {
+      float rows[3][kRows];
 #pragma unroll
-    for (int m = 0; m < 3; m++) lam3[m] = amask ? sm.lam[row_of(leg, m)][el] : 0.f;
-  }
-  if (any) { /* block-uniform: envs without contact add exact zeros (full-mask shuffles inside) */
+      for (int j = 0; j < 4; j++) {
+        float Kj[3][6];
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) Kj[n][i] = __shfl_sync(gm, ln.K[n][i], gbase + j);
+        }
+        assemble_block<NJL>(ln, j, Kj, rows);
+      }
+      pgs_lane_init<NJL>(ln, leg, rows, amask, pl);
+    }
+    const int nc = __popc(amask);
+    nc_sum += nc;
+    for (int it = 0; it < sc.iters; it++) {
+      float res2 = 0.f;
+      sweep_feet += nc;
+#pragma unroll
+      for (int f = 0; f < 4; f++) {
+        if (!((amask >> f) & 1u)) continue;
+        float nv, d, rv;
+        pgs_normal_candidate(pl, nv, d, rv);
+        d = __shfl_sync(gm, d, gbase + f);
+        rv = __shfl_sync(gm, rv, gbase + f);
+        if (leg == f) pl.lam[0] = nv;
+        pgs_apply(pl, row_of(f, 0), d);
+        res2 = fmaxf(res2, rv * rv);
+      }
+#pragma unroll
+      for (int f = 0; f < 4; f++) {
+        if (!((amask >> f) & 1u)) continue;
+        if (sc.cone) {
+          float nA, nB, dA, dB, rv;
+          pgs_cone_candidate(pl, sc.mu, nA, nB, dA, dB, rv);
+          dA = __shfl_sync(gm, dA, gbase + f);
+          dB = __shfl_sync(gm, dB, gbase + f);
+          rv = __shfl_sync(gm, rv, gbase + f);
+          if (leg == f) { pl.lam[1] = nA; pl.lam[2] = nB; }
+          pgs_apply(pl, row_of(f, 1), dA);
+          pgs_apply(pl, row_of(f, 2), dB);
+          res2 = fmaxf(res2, rv * rv);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            float nv, d, rv;
+            pgs_pyramid_candidate(pl, sc.mu, q, nv, d, rv);
+            d = __shfl_sync(gm, d, gbase + f);
+            rv = __shfl_sync(gm, rv, gbase + f);
+            if (leg == f) pl.lam[1 + q] = nv;
+            pgs_apply(pl, row_of(f, 1 + q), d);
+            res2 = fmaxf(res2, rv * rv);
+          }
+        }
+      }
+      if (res2 <= sc.res_thr) break;
+    }
+#pragma unroll
+    for (int m = 0; m < 3; m++) lam3[m] = pl.lam[m];
     float part[6], dv0[6];
     impulse_base_part<NJL>(ln, lam3, part);
 #pragma unroll
-    for (int i = 0; i < 6; i++) dv0[i] = sum4(part[i]);
+    for (int i = 0; i < 6; i++) dv0[i] = sum4(gm, part[i]);
     impulse_leg<NJL>(ln, sc, lam3, dv0);
     float dw[3], dvl[3];
     mat3_mulv(bw.R, dv0, dw);
@@ -340,22 +377,9 @@ __global__ void __launch_bounds__(kBlockThreads) step_kernel(const __grid_consta
   __syncthreads();
   const int nsub = (args.mode == MODE_SUBSTEP) ? 1 : sc.frame_skip;
 
-  if (tid >= kLegThreads) { /* ---- solver warp: one env per lane ---- */
-    const int lane = tid - kLegThreads;
-    for (int s = 0; s < nsub; s++) {
-      const int any = __syncthreads_or(0);
-      if (any) {
-        const unsigned fm = __reduce_or_sync(0xffffffffu, sm.mask[lane]);
-        pgs_solve(&sm.B[0][lane], &sm.g0[0][lane], kEnvsPerBlock, sc.iters, sc.cone, sc.mu, fm, &sm.lam[0][lane]);
-        __syncthreads();
-      }
-    }
-    return;
-  }
-
-  /* ---- leg lanes ---- */
   const DevArrays& d = args.d;
   const int el = tid >> 2, leg = tid & 3;
+  const unsigned gm = 0xFu << ((unsigned)tid & 28u);
   const int env = blockIdx.x * kEnvsPerBlock + el;
   const bool valid = env < args.n;
   const int e = valid ? env : args.n - 1;
@@ -398,12 +422,13 @@ __global__ void __launch_bounds__(kBlockThreads) step_kernel(const __grid_consta
     push_history<NJL>(d, sc, D0, e, leg, cur);
   }
 
+  bk.nc_sum = 0; bk.sweep_feet = 0;
   for (int s = 0; s < nsub; s++) {                  /* frame_skip x p.stepSimulation() (solo.py:264-265) */
     const bool torque_on = (s == 0) || sc.torque_hold; /* SURVEY F4 */
     float tau_s[NJL];
 #pragma unroll
     for (int k = 0; k < NJL; k++) tau_s[k] = torque_on ? tau[k] : 0.f;
-    group_substep<NJL>(sm, args.mc, sc, el, leg, st, ln, tau_s, cforce);
+    group_substep<NJL>(sm.leg[leg], args.mc, sc, leg, st, ln, tau_s, cforce, bk.nc_sum, bk.sweep_feet);
   }
 
   float progress = 0.f;
@@ -430,7 +455,7 @@ __global__ void __launch_bounds__(kBlockThreads) step_kernel(const __grid_consta
       sq += (sc.task == 0) ? fabsf(ln.q[k]) : ln.q[k] * ln.q[k];
       sa += act[k] * act[k];
     }
-    sq = sum4(sq); sa = sum4(sa);
+    sq = sum4(gm, sq); sa = sum4(gm, sa);
     StepOutcome o = step_outcome(sc, st, 4 * NJL, sq, sa, progress, bk);
     if (valid && leg == 0) {
       args.reward[e] = o.reward;
@@ -588,6 +613,13 @@ __global__ void set_goal_kernel(DevArrays d, int n, const float* goals) {
   b[kBasePot] = sqrtf(dx * dx + dy * dy);
 }
 
+__global__ void work_kernel(DevArrays d, int n, int* out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  out[2 * e] = d.book[e].nc_sum;
+  out[2 * e + 1] = d.book[e].sweep_feet;
+}
+
 __global__ void contacts_kernel(DevArrays d, SimConst sc, int n, float* out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * 4) return;
@@ -628,9 +660,10 @@ __global__ void fd_kernel(ModelConst mc, SimConst sc, int n, const float* state,
   Sym6 IA;
   float pA[6], a0[6], qdd[NJL], aw[3], al[3];
   leg_inward<NJL>(sleg[leg], sc, bw, ln, tau, IA, pA);
-  sum4_sym6(IA);
+  const unsigned gm = 0xFu << ((unsigned)threadIdx.x & 28u);
+  sum4_sym6(gm, IA);
 #pragma unroll
-  for (int i = 0; i < 6; i++) pA[i] = sum4(pA[i]);
+  for (int i = 0; i < 6; i++) pA[i] = sum4(gm, pA[i]);
   base_solve(mc, sc, bw, IA, pA, a0);
   leg_outward<NJL>(ln, a0, qdd);
   base_world_acc(sc, bw, a0, aw, al);
@@ -880,7 +913,13 @@ int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_
     if (h->njl == 3) fill_cache_kernel<3><<<1, 32, 0, s>>>(h->d, h->K, H, h->D0);
     else fill_cache_kernel<2><<<1, 32, 0, s>>>(h->d, h->K, H, h->D0);
     h->launches++;
+    /* the cache-generation envs leave no trace: counters, goals and states start from zero */
     CUDA_TRY(h, cudaMemsetAsync(h->d.book, 0, cap * sizeof(EnvBook), s));
+    CUDA_TRY(h, cudaMemsetAsync(h->d.base, 0, cap * kBaseStride * sizeof(float), s));
+    CUDA_TRY(h, cudaMemsetAsync(h->d.q, 0, cap * 4 * h->njl * sizeof(float), s));
+    CUDA_TRY(h, cudaMemsetAsync(h->d.qd, 0, cap * 4 * h->njl * sizeof(float), s));
+    CUDA_TRY(h, cudaMemsetAsync(h->d.cforce, 0, cap * 4 * sizeof(float), s));
+    CUDA_TRY(h, cudaMemsetAsync(h->d.hist, 0, (cap * (H > 0 ? H : 1)) * h->D0 * sizeof(float), s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     CUDA_TRY(h, cudaGetLastError());
   }
@@ -978,6 +1017,14 @@ int solo_get_contacts(SoloHandle* h, float* d_out, void* stream) {
   if (!h || !d_out) return fail(h, SOLO_E_ARG, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   contacts_kernel<<<(h->n * 4 + 127) / 128, 128, 0, s>>>(h->d, h->sc, h->n, d_out);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_get_work_counters(SoloHandle* h, int32_t* d_out, void* stream) {
+  if (!h || !d_out) return fail(h, SOLO_E_ARG, "null argument");
+  work_kernel<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d, h->n, d_out);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return SOLO_OK;

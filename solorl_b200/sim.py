@@ -112,6 +112,12 @@ class SoloSim:
         _lib.check(self.L.solo_get_contacts(self.h, _ptr(out), self._stream()), self.h)
         return out
 
+    def get_work_counters(self):
+        """int32 [N,2]: (feet-in-contact, feet-in-contact x PGS sweeps) summed over the substeps of the last step."""
+        out = torch.empty(self.n, 2, dtype=torch.int32, device=self.device)
+        _lib.check(self.L.solo_get_work_counters(self.h, _ptr(out), self._stream()), self.h)
+        return out
+
     def forward_dynamics(self, state, tau):
         s = self._f32(state, (self.n, 13 + 2 * self.nj))
         t = self._f32(tau, (self.n, self.nj))

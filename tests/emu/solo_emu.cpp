@@ -92,13 +92,44 @@ static void emu_substep(Emu* e, const float* tau) {
   float lam[kRows];
   for (int r = 0; r < kRows; r++) lam[r] = 0.f;
   if (mask) {
-    float B[kRows * kRows], g0[kRows];
+    PgsLane pl[4];
     for (int l = 0; l < 4; l++) {
       float rows[3][kRows];
       for (int j = 0; j < 4; j++) assemble_block<NJL>(ln[l], j, ln[j].K, rows);
-      assemble_finish<NJL>(ln[l], l, rows, mask, B, g0, 1);
+      pgs_lane_init<NJL>(ln[l], l, rows, mask, pl[l]);
     }
-    pgs_solve(B, g0, 1, sc.iters, sc.cone, sc.mu, mask, lam);
+    for (int it = 0; it < sc.iters; it++) {
+      float res2 = 0.f;
+      for (int f = 0; f < 4; f++) {
+        if (!((mask >> f) & 1u)) continue;
+        float nv, d, rv;
+        pgs_normal_candidate(pl[f], nv, d, rv);   /* owner lane; "shuffle" = plain read */
+        pl[f].lam[0] = nv;
+        for (int l = 0; l < 4; l++) pgs_apply(pl[l], row_of(f, 0), d);
+        res2 = fmaxf(res2, rv * rv);
+      }
+      for (int f = 0; f < 4; f++) {
+        if (!((mask >> f) & 1u)) continue;
+        if (sc.cone) {
+          float nA, nB, dA, dB, rv;
+          pgs_cone_candidate(pl[f], sc.mu, nA, nB, dA, dB, rv);
+          pl[f].lam[1] = nA; pl[f].lam[2] = nB;
+          for (int l = 0; l < 4; l++) { pgs_apply(pl[l], row_of(f, 1), dA); pgs_apply(pl[l], row_of(f, 2), dB); }
+          res2 = fmaxf(res2, rv * rv);
+        } else {
+          for (int q = 0; q < 2; q++) {
+            float nv, d, rv;
+            pgs_pyramid_candidate(pl[f], sc.mu, q, nv, d, rv);
+            pl[f].lam[1 + q] = nv;
+            for (int l = 0; l < 4; l++) pgs_apply(pl[l], row_of(f, 1 + q), d);
+            res2 = fmaxf(res2, rv * rv);
+          }
+        }
+      }
+      if (res2 <= sc.res_thr) break;
+    }
+    for (int l = 0; l < 4; l++)
+      for (int m = 0; m < 3; m++) lam[row_of(l, m)] = pl[l].lam[m];
   }
   float dv0[6];
   {

