@@ -8,9 +8,9 @@
  * dependent-latency problem, so the design minimises the per-warp instruction chain rather than
  * occupancy).  All cross-leg traffic — the sum of the four legs' articulated inertias into the
  * floating base, the exchange of IA0^-1 P blocks for the Delassus rows, and the one-value
- * broadcast per projected-Gauss-Seidel row relaxation — is register shuffles restricted to the
- * env's 4-lane group, so a group never waits for another env; there is no block barrier and no
- * shared-memory staging in the step (shared memory only holds the per-leg model constants).
+ * broadcast per projected-Gauss-Seidel row relaxation — is full-mask register shuffles of a
+ * converged warp; there is no block barrier and no shared-memory staging in the step (shared
+ * memory only holds the per-leg model constants).
  *
  * HBM layout (structure of arrays, fp32):
  *   base  [cap][16]  : pos3 quat4 linvel3 angvel3 goal2 potential1   (4 x float4 per env)
@@ -87,19 +87,19 @@ struct Smem {
   LegConst leg[4];
 };
 
-/* sum over the four lanes of an env (xor butterfly inside the 4-lane group `gm`) */
-__device__ __forceinline__ float sum4(unsigned gm, float x) {
-  x += __shfl_xor_sync(gm, x, 1);
-  x += __shfl_xor_sync(gm, x, 2);
+/* sum over the four lanes of an env (xor butterfly; the whole warp is converged) */
+__device__ __forceinline__ float sum4(float x) {
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  x += __shfl_xor_sync(0xffffffffu, x, 2);
   return x;
 }
-__device__ __forceinline__ void sum4_sym6(unsigned gm, Sym6& I) {
+__device__ __forceinline__ void sum4_sym6(Sym6& I) {
 #pragma unroll
-  for (int i = 0; i < 6; i++) I.A[i] = sum4(gm, I.A[i]);
+  for (int i = 0; i < 6; i++) I.A[i] = sum4(I.A[i]);
 #pragma unroll
-  for (int i = 0; i < 9; i++) I.H[i] = sum4(gm, I.H[i]);
+  for (int i = 0; i < 9; i++) I.H[i] = sum4(I.H[i]);
 #pragma unroll
-  for (int i = 0; i < 6; i++) I.M[i] = sum4(gm, I.M[i]);
+  for (int i = 0; i < 6; i++) I.M[i] = sum4(I.M[i]);
 }
 
 /* ---- the pieces of one D0-row of the observation that a lane produces -------------- */
@@ -256,22 +256,25 @@ __device__ __forceinline__ void begin_reset(const DevArrays& d, const SimConst& 
   potential = (sc.task == 2) ? calc_potential(st, goal) : 0.f;   /* solo.py:176 */
 }
 
-/* One Bullet-equivalent substep for the four lanes of an env (see solo_core.cuh). */
+/* One Bullet-equivalent substep for the four lanes of an env (see solo_core.cuh).
+ * Control flow is kept WARP-uniform (skip masks and the sweep-loop exit are warp votes, envs that
+ * have nothing to do contribute exact zeros) so that every shuffle is a full-mask shuffle of a
+ * converged warp: group-masked shuffles cost a WARPSYNC each and let the 4-lane groups drift apart. */
 template <int NJL>
 __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelConst& mc, const SimConst& sc,
                                               int leg, BaseState& st, Lane<NJL>& ln, const float* tau, float& cforce,
                                               int& nc_sum, int& sweep_feet) {
+  const unsigned kFull = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned gbase = lane & ~3u;
-  const unsigned gm = 0xFu << gbase;
   BaseWork bw;
   base_prepare(st, bw);
   Sym6 IA;
   float pA[6], a0[6];
   leg_inward<NJL>(lc, sc, bw, ln, tau, IA, pA);
-  sum4_sym6(gm, IA);
+  sum4_sym6(IA);
 #pragma unroll
-  for (int i = 0; i < 6; i++) pA[i] = sum4(gm, pA[i]);
+  for (int i = 0; i < 6; i++) pA[i] = sum4(pA[i]);
   base_solve(mc, sc, bw, IA, pA, a0);
   {
     float qdd[NJL], aw[3], al[3];
@@ -282,11 +285,12 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
     for (int k = 0; k < NJL; k++) ln.qd[k] = clampf(ln.qd[k] + sc.dt * qdd[k], -sc.vmax, sc.vmax);
   }
   contact_setup<NJL>(lc, mc, sc, st, bw, ln);
-  unsigned amask = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) amask |= (unsigned)(__shfl_sync(gm, ln.active, gbase + j) != 0) << j;
+  const unsigned ball = __ballot_sync(kFull, ln.active != 0);
+  const unsigned amask = (ball >> gbase) & 0xFu;                 /* feet in contact of this env */
+  const unsigned wmask = (ball | (ball >> 4) | (ball >> 8) | (ball >> 12) | (ball >> 16) | (ball >> 20) |
+                          (ball >> 24) | (ball >> 28)) & 0xFu;     /* ... of any env of the warp */
   float lam3[3] = {0.f, 0.f, 0.f};
-  if (amask) {   /* uniform over the env's four lanes */
+  if (wmask) {   /* warp-uniform */
     PgsLane pl;
     {
       float rows[3][kRows];
@@ -296,7 +300,7 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
 #pragma unroll
         for (int n = 0; n < 3; n++) {
 #pragma unroll
-          for (int i = 0; i < 6; i++) Kj[n][i] = __shfl_sync(gm, ln.K[n][i], gbase + j);
+          for (int i = 0; i < 6; i++) Kj[n][i] = __shfl_sync(kFull, ln.K[n][i], gbase + j);
         }
         assemble_block<NJL>(ln, j, Kj, rows);
       }
@@ -304,54 +308,57 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
     }
     const int nc = __popc(amask);
     nc_sum += nc;
+    bool conv = (amask == 0);          /* env-uniform: the sweep loop of this env has ended */
     for (int it = 0; it < sc.iters; it++) {
-      float res2 = 0.f;
-      sweep_feet += nc;
+      float res_own = 0.f;             /* largest |velocity residual| among the rows this lane relaxed */
+      sweep_feet += conv ? 0 : nc;
 #pragma unroll
       for (int f = 0; f < 4; f++) {
-        if (!((amask >> f) & 1u)) continue;
+        if (!((wmask >> f) & 1u)) continue;
         float nv, d, rv;
         pgs_normal_candidate(pl, nv, d, rv);
-        d = __shfl_sync(gm, d, gbase + f);
-        rv = __shfl_sync(gm, rv, gbase + f);
-        if (leg == f) pl.lam[0] = nv;
-        pgs_apply(pl, row_of(f, 0), d);
-        res2 = fmaxf(res2, rv * rv);
+        d = conv ? 0.f : d;
+        const float db = __shfl_sync(kFull, d, gbase + f);
+        if (leg == f && !conv) { pl.lam[0] = nv; res_own = fmaxf(res_own, fabsf(rv)); }
+        pgs_apply(pl, row_of(f, 0), db);
       }
 #pragma unroll
       for (int f = 0; f < 4; f++) {
-        if (!((amask >> f) & 1u)) continue;
+        if (!((wmask >> f) & 1u)) continue;
         if (sc.cone) {
           float nA, nB, dA, dB, rv;
           pgs_cone_candidate(pl, sc.mu, nA, nB, dA, dB, rv);
-          dA = __shfl_sync(gm, dA, gbase + f);
-          dB = __shfl_sync(gm, dB, gbase + f);
-          rv = __shfl_sync(gm, rv, gbase + f);
-          if (leg == f) { pl.lam[1] = nA; pl.lam[2] = nB; }
-          pgs_apply(pl, row_of(f, 1), dA);
-          pgs_apply(pl, row_of(f, 2), dB);
-          res2 = fmaxf(res2, rv * rv);
+          dA = conv ? 0.f : dA;
+          dB = conv ? 0.f : dB;
+          const float dAb = __shfl_sync(kFull, dA, gbase + f);
+          const float dBb = __shfl_sync(kFull, dB, gbase + f);
+          if (leg == f && !conv) { pl.lam[1] = nA; pl.lam[2] = nB; res_own = fmaxf(res_own, fabsf(rv)); }
+          pgs_apply(pl, row_of(f, 1), dAb);
+          pgs_apply(pl, row_of(f, 2), dBb);
         } else {
 #pragma unroll
           for (int q = 0; q < 2; q++) {
             float nv, d, rv;
             pgs_pyramid_candidate(pl, sc.mu, q, nv, d, rv);
-            d = __shfl_sync(gm, d, gbase + f);
-            rv = __shfl_sync(gm, rv, gbase + f);
-            if (leg == f) pl.lam[1 + q] = nv;
-            pgs_apply(pl, row_of(f, 1 + q), d);
-            res2 = fmaxf(res2, rv * rv);
+            d = conv ? 0.f : d;
+            const float db = __shfl_sync(kFull, d, gbase + f);
+            if (leg == f && !conv) { pl.lam[1 + q] = nv; res_own = fmaxf(res_own, fabsf(rv)); }
+            pgs_apply(pl, row_of(f, 1 + q), db);
           }
         }
       }
-      if (res2 <= sc.res_thr) break;
+      /* end of sweep: largest residual of the env (max over its four lanes), Bullet's exit test */
+      float r = fmaxf(res_own, __shfl_xor_sync(kFull, res_own, 1));
+      r = fmaxf(r, __shfl_xor_sync(kFull, r, 2));
+      conv = conv || (r * r <= sc.res_thr);
+      if (__all_sync(kFull, conv)) break;
     }
 #pragma unroll
     for (int m = 0; m < 3; m++) lam3[m] = pl.lam[m];
     float part[6], dv0[6];
     impulse_base_part<NJL>(ln, lam3, part);
 #pragma unroll
-    for (int i = 0; i < 6; i++) dv0[i] = sum4(gm, part[i]);
+    for (int i = 0; i < 6; i++) dv0[i] = sum4(part[i]);
     impulse_leg<NJL>(ln, sc, lam3, dv0);
     float dw[3], dvl[3];
     mat3_mulv(bw.R, dv0, dw);
@@ -379,7 +386,6 @@ __global__ void __launch_bounds__(kBlockThreads) step_kernel(const __grid_consta
 
   const DevArrays& d = args.d;
   const int el = tid >> 2, leg = tid & 3;
-  const unsigned gm = 0xFu << ((unsigned)tid & 28u);
   const int env = blockIdx.x * kEnvsPerBlock + el;
   const bool valid = env < args.n;
   const int e = valid ? env : args.n - 1;
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(kBlockThreads) step_kernel(const __grid_consta
       sq += (sc.task == 0) ? fabsf(ln.q[k]) : ln.q[k] * ln.q[k];
       sa += act[k] * act[k];
     }
-    sq = sum4(gm, sq); sa = sum4(gm, sa);
+    sq = sum4(sq); sa = sum4(sa);
     StepOutcome o = step_outcome(sc, st, 4 * NJL, sq, sa, progress, bk);
     if (valid && leg == 0) {
       args.reward[e] = o.reward;
@@ -660,10 +666,9 @@ __global__ void fd_kernel(ModelConst mc, SimConst sc, int n, const float* state,
   Sym6 IA;
   float pA[6], a0[6], qdd[NJL], aw[3], al[3];
   leg_inward<NJL>(sleg[leg], sc, bw, ln, tau, IA, pA);
-  const unsigned gm = 0xFu << ((unsigned)threadIdx.x & 28u);
-  sum4_sym6(gm, IA);
+  sum4_sym6(IA);
 #pragma unroll
-  for (int i = 0; i < 6; i++) pA[i] = sum4(gm, pA[i]);
+  for (int i = 0; i < 6; i++) pA[i] = sum4(pA[i]);
   base_solve(mc, sc, bw, IA, pA, a0);
   leg_outward<NJL>(ln, a0, qdd);
   base_world_acc(sc, bw, a0, aw, al);

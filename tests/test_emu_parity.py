@@ -59,11 +59,11 @@ def test_observation_given_identical_state_1e6(robot, task, H):
     rng = np.random.default_rng(12)
     o, e, _, _ = pair(robot, task=task, H=H)
     for s in random_states(rng, 50, o.nj, vel_scale=0.3):
-        o.set_state(s)
-        e.set_state(s)
-        if task == "pointgoal":
+        if task == "pointgoal":      # goal first: set_state fills the history with the current goal
             o.set_goal(1.5, -1.25)
             e.set_goal(1.5, -1.25)
+        o.set_state(s)
+        e.set_state(s)
         a, b = o.get_observation(), e.get_observation()
         scale = np.maximum(1.0, np.abs(a))
         assert (obs_diff(a, b, o.d0) / scale).max() < TOL_ENV
@@ -84,10 +84,15 @@ def test_reward_given_identical_state_1e6(task, control):
     o, e = OracleEnv(m, p), EmuEnv(m, p)
     for i in range(40):
         s = np.zeros(13 + 24)
-        s[2] = rng.uniform(0.1, 1.5)
-        ang = rng.normal(size=3) * 0.3
-        s[3:7] = [np.sin(ang[0] / 2), 0, 0, np.cos(ang[0] / 2)]
-        s[13:25] = rng.uniform(-1, 1, size=12)
+        if i % 4:                                   # well clear of the ground: no contact rows
+            s[2] = rng.uniform(0.6, 1.5)
+            ang = rng.normal(size=3) * 0.3
+            s[3:7] = [np.sin(ang[0] / 2), 0, 0, np.cos(ang[0] / 2)]
+            s[13:25] = rng.uniform(-1, 1, size=12)
+        else:                                       # below stand_z (0.2): legs folded forward
+            s[2], s[6] = rng.uniform(0.1, 0.19), 1.0
+            s[13:25] = rng.uniform(-0.1, 0.1, size=12)
+            s[14:25:3] += np.pi / 2
         s = s.astype(np.float32).astype(np.float64)
         a = np.zeros(12) if control == "torque" else rng.uniform(-1, 1, size=12)
         if control == "torque":

@@ -100,15 +100,15 @@ def test_observation_given_identical_state_1e6(robot, task, H):
     n = 128
     sim, m, p = make_sim(robot, n, task=task, H=H)
     s = random_states(rng, n, sim.nj, vel_scale=0.3)
-    sim.set_state(cuda(s))
-    if task == "pointgoal":
+    if task == "pointgoal":      # goal first: set_state fills the history with the current goal
         sim.set_goals(cuda(np.tile([1.5, -1.25], (n, 1))))
+    sim.set_state(cuda(s))
     got = sim.get_observation().cpu().numpy()
     o = OracleEnv(m, p)
     for i in range(n):
-        o.set_state(s[i])
         if task == "pointgoal":
             o.set_goal(1.5, -1.25)
+        o.set_state(s[i])
         ref = o.get_observation()
         assert (obs_diff(ref, got[i], o.d0) / np.maximum(1.0, np.abs(ref))).max() < TOL_ENV
     sim.close()
@@ -128,10 +128,15 @@ def test_reward_given_identical_state_1e6(task, control):
         p.kp = p.kd = 0.0
     sim = SoloSim(m, p, n, device=0)
     s = np.zeros((n, 37))
-    s[:, 2] = rng.uniform(0.1, 1.5, size=n)
+    s[:, 2] = rng.uniform(0.6, 1.5, size=n)                 # well clear of the ground: no contact rows
     ang = rng.normal(size=n) * 0.3
     s[:, 3], s[:, 6] = np.sin(ang / 2), np.cos(ang / 2)
     s[:, 13:25] = rng.uniform(-1, 1, size=(n, 12))
+    low = np.arange(n) % 4 == 0                             # below stand_z (0.2): legs folded forward
+    s[low, 2] = rng.uniform(0.1, 0.19, size=low.sum())
+    s[low, 3], s[low, 6] = 0.0, 1.0
+    s[low, 13:25] = rng.uniform(-0.1, 0.1, size=(low.sum(), 12))
+    s[low, 14:25:3] += np.pi / 2
     a = np.zeros((n, 12))
     if control == "torque":
         s[:, 7] = rng.normal(size=n)

@@ -127,9 +127,10 @@ def main():
     e1.close(); e2.close()
 
     # rough timing
-    for name, n in (("solo12", 4096), ("solo8", 4096), ("solo12", 65536)):
+    for name, n, thr in (("solo12", 4096, 1e-7), ("solo12", 4096, 0.0), ("solo8", 4096, 1e-7), ("solo12", 65536, 1e-7),
+                         ("solo12", 262144, 1e-7), ("solo12", 262144, 0.0)):
         cfg = {"model_urdf": name, "mode": "headless", "episode_length": 400, "frame_skip": 4,
-               "control": "torque", "task": "walk", "num_history_stack": 1}
+               "control": "torque", "task": "walk", "num_history_stack": 1, "solver_residual_threshold": thr}
         env = SoloVecEnv(cfg, n, device="cuda:0", seed=1)
         env.reset()
         acts = [torch.rand(n, env.sim.act_dim, device="cuda") * 2 - 1 for _ in range(8)]
@@ -146,7 +147,7 @@ def main():
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1) / K
         con = env.sim.get_contacts()[:, :, 1].sum(1).mean().item()
-        print(f"{name} n={n}: {ms * 1e3:.1f} us/step -> {n / ms * 1e3:.3e} env-steps/s (mean contacts {con:.2f})")
+        print(f"{name} n={n} thr={thr}: {ms * 1e3:.1f} us/step -> {n / ms * 1e3:.3e} env-steps/s (mean contacts {con:.2f})")
         env.close()
 
 
