@@ -93,9 +93,11 @@ SOLO_HD float dot6(const float* a, const float* b) {
   return (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + (a[3] * b[3] + a[4] * b[4] + a[5] * b[5]);
 }
 SOLO_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
-SOLO_HD float solo_rsqrt(float x) {
+SOLO_HD float solo_rsqrt(float x) {   /* x >= 1e-30: one MUFU.RSQ, no denormal fix-up code */
 #if defined(__CUDA_ARCH__)
-  return rsqrtf(x);
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 #else
   return 1.0f / sqrtf(x);
 #endif
@@ -635,14 +637,14 @@ SOLO_HD void pgs_normal_candidate(const PgsLane& pl, float& nv, float& d, float&
 /* candidates for this lane's friction pair (cone) */
 SOLO_HD void pgs_cone_candidate(const PgsLane& pl, float mu, float& nA, float& nB, float& dA, float& dB,
                                 float& rv) {
+  /* Bullet clamps sA to +-|lim sin(atan2(sA,sB))| and sB to +-|lim cos(.)|, i.e. it scales the pair
+   * (sA,sB) back onto the circle of radius lim when it lies outside: (sA,sB) * min(1, lim/|s|). */
   const float lim = mu * pl.lam[0];
   const float sA = pl.g[1], sB = pl.g[2];
-  const float n2 = sA * sA + sB * sB;
-  const float inv = n2 > 0.f ? solo_rsqrt(n2) : 0.f;
-  const float limA = lim * fabsf(sA) * inv;
-  const float limB = n2 > 0.f ? lim * fabsf(sB) * inv : lim;
-  nA = clampf(sA, -limA, limA);
-  nB = clampf(sB, -limB, limB);
+  const float n2 = fmaxf(sA * sA + sB * sB, 1e-30f);
+  const float sc = fminf(lim * solo_rsqrt(n2), 1.0f);
+  nA = sA * sc;
+  nB = sB * sc;
   dA = nA - pl.lam[1];
   dB = nB - pl.lam[2];
   rv = dA * pl.diag[1] + dB * pl.diag[2];

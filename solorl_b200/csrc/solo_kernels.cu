@@ -313,8 +313,7 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
       float res_own = 0.f;             /* largest |velocity residual| among the rows this lane relaxed */
       sweep_feet += conv ? 0 : nc;
 #pragma unroll
-      for (int f = 0; f < 4; f++) {
-        if (!((wmask >> f) & 1u)) continue;
+      for (int f = 0; f < 4; f++) {   /* feet without contact hold zero rows: no skip branches */
         float nv, d, rv;
         pgs_normal_candidate(pl, nv, d, rv);
         d = conv ? 0.f : d;
@@ -324,7 +323,6 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
       }
 #pragma unroll
       for (int f = 0; f < 4; f++) {
-        if (!((wmask >> f) & 1u)) continue;
         if (sc.cone) {
           float nA, nB, dA, dB, rv;
           pgs_cone_candidate(pl, sc.mu, nA, nB, dA, dB, rv);
@@ -347,11 +345,12 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
           }
         }
       }
-      /* end of sweep: largest residual of the env (max over its four lanes), Bullet's exit test */
-      float r = fmaxf(res_own, __shfl_xor_sync(kFull, res_own, 1));
-      r = fmaxf(r, __shfl_xor_sync(kFull, r, 2));
-      conv = conv || (r * r <= sc.res_thr);
-      if (__all_sync(kFull, conv)) break;
+      /* end of sweep, Bullet's exit test: the env is done when every row residual of the sweep is
+       * within the threshold, i.e. when each of its four lanes is; one ballot serves the env test
+       * and the warp-wide loop exit */
+      const unsigned okb = __ballot_sync(kFull, conv || (res_own * res_own <= sc.res_thr));
+      conv = conv || (((okb >> gbase) & 0xFu) == 0xFu);
+      if (okb == kFull) break;
     }
 #pragma unroll
     for (int m = 0; m < 3; m++) lam3[m] = pl.lam[m];
