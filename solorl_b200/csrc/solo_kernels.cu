@@ -21,6 +21,8 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <string>
 #include <vector>
@@ -32,8 +34,7 @@
 
 namespace solo {
 
-constexpr int kEnvsPerBlock = 8;
-constexpr int kBlockThreads = 32;
+constexpr int kBlockThreads = 32;   /* one warp per block */
 
 enum { MODE_STEP = 0, MODE_SETTLE = 1, MODE_SUBSTEP = 2 };
 
@@ -370,7 +371,10 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
   for (int k = 0; k < NJL; k++) ln.q[k] += sc.dt * ln.qd[k];
 }
 
-template <int NJL>
+/* EPW = environments per warp (8, 4 or 2).  Below ~2 warps per scheduler the step is latency-bound,
+ * so small batches spread over MORE warps: with EPW < 8 the lanes past 4*EPW mirror the first ones
+ * (same env, same arithmetic, no stores), which keeps every warp vote and shuffle unchanged. */
+template <int NJL, int EPW>
 __global__ void __launch_bounds__(kBlockThreads) step_kernel(const __grid_constant__ StepArgs args) {
   __shared__ Smem sm;
   const int tid = threadIdx.x;
@@ -384,9 +388,9 @@ __global__ void __launch_bounds__(kBlockThreads) step_kernel(const __grid_consta
   const int nsub = (args.mode == MODE_SUBSTEP) ? 1 : sc.frame_skip;
 
   const DevArrays& d = args.d;
-  const int el = tid >> 2, leg = tid & 3;
-  const int env = blockIdx.x * kEnvsPerBlock + el;
-  const bool valid = env < args.n;
+  const int el = (tid >> 2) % EPW, leg = tid & 3;
+  const int env = blockIdx.x * EPW + el;
+  const bool valid = ((tid >> 2) < EPW) && env < args.n;
   const int e = valid ? env : args.n - 1;
   const long long gid = args.env_id_offset + e;
   const int D0 = args.D0;
@@ -749,6 +753,7 @@ struct SoloHandle {
   ModelConst mc;
   SimConst sc;
   int n, njl, nj, A, D0, D, device, K, cap;
+  int epw;   /* environments per warp of the step kernel (8, 4 or 2) */
   uint64_t seed;
   long long env_id_offset;
   float goal_radius;
@@ -784,11 +789,26 @@ static StepArgs make_step_args(SoloHandle* h, int mode, int n, const float* in, 
   a.force_settle = -1;
   return a;
 }
+template <int EPW>
+static void launch_step_epw(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
+  const int blocks = (a.n + EPW - 1) / EPW;
+  if (h->njl == 3) step_kernel<3, EPW><<<blocks, kBlockThreads, 0, s>>>(a);
+  else step_kernel<2, EPW><<<blocks, kBlockThreads, 0, s>>>(a);
+}
 static void launch_step(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
-  const int blocks = (a.n + kEnvsPerBlock - 1) / kEnvsPerBlock;
-  if (h->njl == 3) step_kernel<3><<<blocks, kBlockThreads, 0, s>>>(a);
-  else step_kernel<2><<<blocks, kBlockThreads, 0, s>>>(a);
+  if (h->epw == 2) launch_step_epw<2>(h, a, s);
+  else if (h->epw == 4) launch_step_epw<4>(h, a, s);
+  else launch_step_epw<8>(h, a, s);
   h->launches++;
+}
+/* Environments per warp.  Measured on B200 (profiles/r1_sweep_epw.txt): full warps win at every
+ * batch size, because a warp's step time is set by its own dependent chain and does not shrink when
+ * lanes idle; the narrower variants stay selectable (SOLO_ENVS_PER_WARP) for experiments. */
+static int choose_epw(int n, int device) {
+  (void)n; (void)device;
+  const char* ev = getenv("SOLO_ENVS_PER_WARP");
+  if (ev) { int v = atoi(ev); if (v == 2 || v == 4 || v == 8) return v; }
+  return 8;
 }
 static ResetArgs make_reset_args(SoloHandle* h, int n, const uint8_t* mask, float* obs) {
   ResetArgs a;
@@ -871,6 +891,7 @@ int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_
   h->device = device; h->seed = seed; h->env_id_offset = env_id_offset;
   h->goal_radius = (float)params->goal_radius;
   h->was_reset = false; h->launches = 0;
+  h->epw = choose_epw(num_envs, device);
   h->K = params->settle_max - params->settle_min; if (h->K < 1) h->K = 1;
   h->cap = num_envs > h->K ? num_envs : h->K;
   h->s_act = h->s_obs = h->s_rew = h->s_done = nullptr;
