@@ -1,0 +1,223 @@
+"""PPO driver with the behaviour of the reference's ``agents/ppo/train.py:21-162`` on the GPU vec-env.
+
+Same loop — rollout of ``num_steps`` vec-env steps, GAE, clipped-surrogate update, linear LR decay,
+curriculum hook, checkpoints ``solo_{steps}.pt`` / ``solo.pt`` holding ``{'update','state_dict',
+'ob_rms'}`` (train.py:121-131) — with three changes to the data path:
+
+* nothing leaves the device during a rollout: the reference reads ``done[i].item()`` and an info dict
+  for every env and step (train.py:90-100); here finished episodes are folded into device-side
+  accumulators from ``solo_episode_stats`` and read once per log interval;
+* the whole rollout (policy act -> env step -> buffer append, ``num_steps`` times) is captured in ONE
+  CUDA graph and replayed, so the ~25 small launches per step cost no CPU time;
+* under ``torchrun`` every rank owns an env shard and the PPO update all-reduces gradients
+  (``agents/ppo.py``); rank 0 logs and checkpoints.
+"""
+from __future__ import annotations
+
+import os
+import time
+from types import SimpleNamespace
+
+import torch
+
+from ..envs import SoloBaseEnv, make_vec_envs
+from . import utils
+from .policy import Policy
+from .ppo import PPO, broadcast_parameters, dist_ready
+from .storage import OPBuffer
+
+_DR = ("dr/stand_rew", "dr/joint_pose_rew", "dr/torque_rew", "dr/roll_pitch_balance_rew", "dr/progress_rew")
+
+
+class EpisodeTracker:
+    """Device-side statistics of finished episodes (what train.py:90-100 appends to its deques)."""
+
+    def __init__(self, device):
+        self.device = device
+        # count, sum last-step reward, sum return, sum length, sum success, 5 x dr sums
+        self.acc = torch.zeros(10, dtype=torch.float64, device=device)
+        self._ext0 = torch.tensor([float("inf"), float("-inf"), 0.0], dtype=torch.float32, device=device)
+        self.ext = self._ext0.clone()      # min return, max return, max length
+
+    def clear(self):
+        """In place: the tensors are baked into the captured rollout graph."""
+        self.acc.zero_()
+        self.ext.copy_(self._ext0)
+
+    def update(self, sim, done):
+        f, i = sim.episode_stats_device()
+        m = done > 0.5
+        md = m.to(torch.float64)
+        cols = torch.stack([torch.ones_like(md), f[:, 0].double(), f[:, 1].double(), i[:, 2].double(),
+                            i[:, 3].double(), f[:, 6].double(), f[:, 7].double(), f[:, 8].double(),
+                            f[:, 9].double(), f[:, 10].double()], dim=0)
+        self.acc.add_((cols * md).sum(dim=1))
+        ret = f[:, 1]
+        lo = torch.where(m, ret, torch.full_like(ret, float("inf"))).min()
+        hi = torch.where(m, ret, torch.full_like(ret, float("-inf"))).max()
+        ln = torch.where(m, i[:, 2].float(), torch.zeros_like(ret)).max()
+        self.ext.copy_(torch.stack([torch.minimum(self.ext[0], lo), torch.maximum(self.ext[1], hi),
+                                    torch.maximum(self.ext[2], ln)]))
+
+    def fetch(self, clear=True):
+        """One host sync; totals are summed over ranks when torch.distributed is up."""
+        acc, ext = self.acc.clone(), self.ext.clone()
+        if dist_ready():
+            torch.distributed.all_reduce(acc)
+            mn, mx = ext[:1].clone(), ext[1:].clone()
+            torch.distributed.all_reduce(mn, op=torch.distributed.ReduceOp.MIN)
+            torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+            ext = torch.cat([mn, mx])
+        a, e = acc.tolist(), ext.tolist()
+        n = max(a[0], 1.0)
+        out = {"episodes": int(a[0]), "episode_reward": a[1] / n, "episode_return": a[2] / n,
+               "episode_length": a[3] / n, "success": a[4] / n,
+               "return_min": e[0], "return_max": e[1], "length_max": e[2]}
+        for k, v in zip(_DR, a[5:]):
+            out[k] = v / n
+        if clear:
+            self.clear()
+        return out
+
+
+class Rollout:
+    """``num_steps`` x (act, env.step, append), eager or as one replayed CUDA graph."""
+
+    def __init__(self, envs, actor_critic, buf, tracker, num_steps, use_graph=True):
+        self.envs, self.ac, self.buf, self.tracker, self.T = envs, actor_critic, buf, tracker, num_steps
+        self.sim = envs.envs.venv.sim
+        self.graph = None
+        self.use_graph = use_graph
+
+    def _run(self):
+        for t in range(self.T):
+            with torch.no_grad():
+                value, action, logp = self.ac.act(self.buf.obs[t])
+                obs, reward, done, _infos = self.envs.step(action)
+                self.tracker.update(self.sim, done)
+                self.buf.append(obs, action, logp, value, reward, (1.0 - done).unsqueeze(-1))
+
+    def __call__(self):
+        if not self.use_graph:
+            return self._run()
+        if self.graph is None:
+            try:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._run()                        # warm-up on a side stream (allocator, lazy init)
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run()
+                self.graph = g
+                # capture does not execute: the rollout of THIS call is the eager warm-up above, which
+                # was a regular rollout from buf.obs[0]; later calls replay the graph
+            except Exception as e:                     # pragma: no cover - capture is best effort
+                print(f"[ppo] CUDA graph capture failed ({e}); running the rollout eagerly", flush=True)
+                self.use_graph = False
+                self.graph = None
+                return self._run()
+            return
+        self.graph.replay()
+
+
+def default_args(**kw):
+    """The argparse defaults of training/train_ppo.py:9-45 as a namespace (for programmatic use)."""
+    a = dict(num_agents=32, output_size=64, hidden_size=64, no_cuda=False, env_name="base", gamma=0.99, tau=0.95,
+             clip_param=0.1, ppo_epoch=10, mini_batch_size=32, lr=1e-3, l2_coef=0.0, value_loss_coef=0.5,
+             entropy_coef=0.01, max_grad_norm=0.5, clip_value_loss=False, use_linear_lr_decay=False, use_gae=False,
+             num_env_steps=int(1e6), seed=2301, curriculum_schedule=0, log_interval=10, logdir=None,
+             base_checkpoint=None, timestamp=None, save_interval=20, task=None, num_steps=None, cuda_graph=True,
+             max_seconds=None, target_return=None)
+    a.update(kw)
+    return SimpleNamespace(**a)
+
+
+def train(args, config, env_constructor=SoloBaseEnv, writer=None):
+    """Returns a dict with the final statistics (the reference calls sys.exit() instead, train.py:162)."""
+    rank = torch.distributed.get_rank() if dist_ready() else 0
+    world = torch.distributed.get_world_size() if dist_ready() else 1
+    torch.manual_seed(args.seed + rank)
+    torch.cuda.manual_seed_all(args.seed + rank)
+    device = torch.device("cuda", torch.cuda.current_device())
+    num_steps = int(args.num_steps or config["episode_length"])        # train_ppo.py:62-63
+    N = int(args.num_agents)
+
+    envs = make_vec_envs(config, N, env_constructor, args.gamma, device, seed=args.seed,
+                         env_id_offset=rank * N)
+    action_dim = envs.action_space.shape[0]
+    base = torch.load(args.base_checkpoint) if args.base_checkpoint is not None else None
+    actor_critic = Policy(envs.observation_space.shape, envs.action_space, base, {"hidden_size": args.hidden_size})
+    actor_critic.to(device)
+    broadcast_parameters(actor_critic)
+    agent = PPO(actor_critic, args.clip_param, args.ppo_epoch, args.mini_batch_size, args.value_loss_coef,
+                args.entropy_coef, lr=args.lr, l2_coef=args.l2_coef, max_grad_norm=args.max_grad_norm)
+    buf = OPBuffer(num_steps, N, envs.observation_space.shape, action_dim, device)
+    buf.obs[0].copy_(envs.reset())
+    tracker = EpisodeTracker(device)
+    rollout = Rollout(envs, actor_critic, buf, tracker, num_steps, use_graph=getattr(args, "cuda_graph", True))
+
+    num_updates = max(int(args.num_env_steps) // num_steps // N // world, 1)
+    start = time.time()
+    last = {"episodes": 0}
+    history = []
+    j = 0
+    for j in range(num_updates):
+        if args.use_linear_lr_decay:
+            utils.update_linear_schedule(agent.optimizer, j, num_updates, args.lr)
+        rollout()
+        with torch.no_grad():
+            next_value = actor_critic.get_value(buf.obs[-1]).detach()
+        buf.compute_returns(next_value, args.use_gae, args.gamma, args.tau)
+        value_loss, action_loss, dist_entropy = agent.update(buf)
+        buf.reset()
+        if args.curriculum_schedule and (j + 1) % args.curriculum_schedule == 0:
+            envs.increment_curriculum()
+        total_num_steps = (j + 1) * N * num_steps * world
+        last_update = j == num_updates - 1
+        if (j % args.save_interval == 0 or last_update) and args.logdir is not None and rank == 0:
+            save_checkpoint(args.logdir, j, actor_critic, envs, total_num_steps)
+        stop = False
+        if j % args.log_interval == 0 or last_update:
+            st = tracker.fetch()
+            elapsed = time.time() - start
+            st.update(update=j, steps=total_num_steps, seconds=elapsed, fps=total_num_steps / max(elapsed, 1e-9),
+                      value_loss=value_loss, action_loss=action_loss, entropy=dist_entropy)
+            history.append(st)
+            last = st
+            if rank == 0:
+                print("Updates {}, num timesteps {}, FPS {}\n {} training episodes: mean return {:.2f} (min {:.2f} max {:.2f}), "
+                      "mean last-step reward {:.3f}, mean/max length {:.0f}/{:.0f}, mean success {:.2f}\n"
+                      " entropy {:.2f} value loss {:.3f} action loss {:.4f}".format(
+                          j, total_num_steps, int(st["fps"]), st["episodes"], st["episode_return"], st["return_min"],
+                          st["return_max"], st["episode_reward"], st["episode_length"], st["length_max"], st["success"],
+                          dist_entropy, value_loss, action_loss), flush=True)
+                if writer is not None:
+                    utils.log(writer, value_loss, "Loss/value", total_num_steps)
+                    utils.log(writer, action_loss, "Loss/action", total_num_steps)
+                    utils.log(writer, dist_entropy, "Loss/entropy", total_num_steps)
+                    utils.log(writer, st["episode_reward"], "Episode/reward", total_num_steps)
+                    utils.log(writer, st["episode_return"], "Episode/return", total_num_steps)
+                    utils.log(writer, st["success"], "Episode/success_mean", total_num_steps)
+                    utils.log(writer, st["episode_length"], "Episode/length", total_num_steps)
+                    for k in _DR:
+                        utils.log(writer, st[k], k, total_num_steps)
+            if args.target_return is not None and st["episodes"] > 0 and st["episode_return"] >= args.target_return:
+                stop = True
+            if args.max_seconds is not None and elapsed >= args.max_seconds:
+                stop = True
+        if stop:
+            break
+    if args.logdir is not None and rank == 0:
+        save_checkpoint(args.logdir, j, actor_critic, envs, (j + 1) * N * num_steps * world)
+    envs.close()
+    return {"last": last, "history": history, "actor_critic": actor_critic, "updates": j + 1,
+            "seconds": time.time() - start}
+
+
+def save_checkpoint(logdir, update, actor_critic, envs, total_num_steps):
+    os.makedirs(logdir, exist_ok=True)
+    blob = {"update": update, "state_dict": actor_critic.state_dict(), "ob_rms": getattr(envs.envs, "ob_rms", None)}
+    torch.save(blob, os.path.join(logdir, "solo_{}.pt".format(total_num_steps)))
+    torch.save(blob, os.path.join(logdir, "solo.pt"))

@@ -173,8 +173,9 @@ class VecNormalize:
 
     def step(self, actions):
         obs, rews, news, infos = self.venv.step(actions)
-        self.ret = self.ret * self.gamma + rews            # running_mean_std.py:98
-        self.ret = torch.where(news > 0.5, torch.zeros_like(self.ret), self.ret)   # :105
+        # in place, so that a CUDA graph captured around step() keeps updating the same tensor
+        self.ret.mul_(self.gamma).add_(rews)               # running_mean_std.py:98
+        self.ret.mul_((news <= 0.5).to(self.ret.dtype))    # :105
         return obs, rews, news, infos
 
     def reset(self):

@@ -92,3 +92,34 @@ for obs_dim, act_dim in ((76, 12), (60, 8), (84, 12), (30, 8)):
 with open(os.path.join(here, "policy_shapes.json"), "w") as f:
     json.dump(shapes, f, indent=1)
 print("golden written:", {k: v["n_params"] for k, v in shapes.items()})
+
+# ---- Policy forward + one PPO update (reference agents/ppo/policy.py, ppo.py, storage.py) --------
+# Full-batch mini-batches (mini_batch_size = T*N) make the update independent of the sampler's order.
+ref_ppo = load(os.path.join(ref, "agents", "ppo", "ppo.py"), "ref_ppo")
+torch.manual_seed(5)
+T, N, D, A = 6, 8, 76, 12
+pol = policy.Policy((D,), Box(A), None, {"hidden_size": 64})
+with torch.no_grad():
+    pol.pi_dist.logstd.copy_(torch.randn(A) * 0.3)
+init_sd = {k: v.clone() for k, v in pol.state_dict().items()}
+gen = torch.Generator().manual_seed(6)
+buf = storage.OPBuffer(T, N, (D,), A, torch.device("cpu"))
+buf.obs.copy_(torch.randn(T + 1, N, D, generator=gen))
+buf.actions.copy_(torch.randn(T, N, A, generator=gen))
+with torch.no_grad():
+    v, lp, ent = pol.evaluate_actions(buf.obs[:-1].reshape(-1, D), buf.actions.reshape(-1, A))
+buf.value_preds[:-1].copy_(v.reshape(T, N, 1) + 0.05 * torch.randn(T, N, 1, generator=gen))
+buf.action_log_probs.copy_(lp.reshape(T, N, 1) + 0.05 * torch.randn(T, N, 1, generator=gen))
+buf.returns.copy_(torch.randn(T + 1, N, 1, generator=gen))
+agent = ref_ppo.PPO(pol, 0.1, 3, T * N, 0.5, 0.01, lr=1e-3, l2_coef=0.0, max_grad_norm=0.5)
+losses = agent.update(buf)
+blob = {"meta": np.array([T, N, D, A]), "losses": np.array(losses, dtype=np.float64),
+        "fwd_value": v.numpy(), "fwd_logp": lp.numpy(), "fwd_entropy": np.array(float(ent)),
+        "obs": buf.obs.numpy(), "actions": buf.actions.numpy(), "value_preds": buf.value_preds.numpy(),
+        "action_log_probs": buf.action_log_probs.numpy(), "returns": buf.returns.numpy()}
+for k, t in init_sd.items():
+    blob["init/" + k] = t.numpy()
+for k, t in pol.state_dict().items():
+    blob["final/" + k] = t.detach().numpy()
+np.savez(os.path.join(here, "ppo_update.npz"), **blob)
+print("ppo_update golden: losses", losses)

@@ -70,3 +70,36 @@ def obs_diff(a, b, d0):
     w = np.minimum(w, np.abs(2.0 - d[..., sl]))
     d[..., sl] = w
     return d
+
+
+def oracle_policy_episodes(policy, cfg, num_envs, seed=0, torch_seed=0, deterministic=False, nthreads=None):
+    """First episode of each of `num_envs` ORACLE envs (fp64 CPU restatement) driven by a torch policy on
+    the CPU: returns (episode_return, episode_length, last_reward) arrays.  The CPU counterpart of
+    solorl_b200.agents.evaluate.evaluate for the episode-return parity test."""
+    import torch
+    from oracle.oracle import OracleVecEnv
+    from solorl_b200.abi import params_from_config
+    from solorl_b200.model import SoloModel
+    m = SoloModel.resolve(cfg["model_urdf"])
+    p = params_from_config(cfg, m)
+    v = OracleVecEnv(m, p, num_envs, seed=seed, nthreads=nthreads)
+    obs = torch.from_numpy(v.reset())
+    g = torch.Generator().manual_seed(torch_seed)
+    ret = np.zeros(num_envs); length = np.zeros(num_envs, dtype=np.int64); last = np.zeros(num_envs)
+    acc = np.zeros(num_envs); steps = np.zeros(num_envs, dtype=np.int64)
+    finished = np.zeros(num_envs, dtype=bool)
+    for t in range(int(cfg["episode_length"]) + 1):
+        with torch.no_grad():
+            value, feat = policy.base(obs)
+            mean, logstd = policy.pi_dist(feat)
+            a = mean if deterministic else mean + torch.randn(mean.shape, generator=g) * logstd.exp()
+        o, r, d = v.step(a.numpy())
+        acc += r; steps += 1
+        newly = (d > 0.5) & ~finished
+        ret[newly] = acc[newly]; length[newly] = steps[newly]; last[newly] = r[newly]
+        finished |= newly
+        if finished.all():
+            break
+        obs = torch.from_numpy(o)
+    assert finished.all()
+    return ret, length, last
