@@ -371,11 +371,14 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
   for (int k = 0; k < NJL; k++) ln.q[k] += sc.dt * ln.qd[k];
 }
 
-/* EPW = environments per warp (8, 4 or 2).  Below ~2 warps per scheduler the step is latency-bound,
+/* MINB = minimum resident blocks per SM asked of the compiler: 1 lets it use 255 registers (8 warps
+ * per SM: shortest per-warp chain, best below ~8k envs), 16 caps it at 128 registers (16 warps per SM,
+ * some spills: +18 % throughput once several waves are resident, profiles/r1_sweep_regs.txt).
+ * EPW = environments per warp (8, 4 or 2).  Below ~2 warps per scheduler the step is latency-bound,
  * so small batches spread over MORE warps: with EPW < 8 the lanes past 4*EPW mirror the first ones
  * (same env, same arithmetic, no stores), which keeps every warp vote and shuffle unchanged. */
-template <int NJL, int EPW>
-__global__ void __launch_bounds__(kBlockThreads) step_kernel(const __grid_constant__ StepArgs args) {
+template <int NJL, int EPW, int MINB>
+__global__ void __launch_bounds__(kBlockThreads, MINB) step_kernel(const __grid_constant__ StepArgs args) {
   __shared__ Smem sm;
   const int tid = threadIdx.x;
   const SimConst& sc = args.sc;
@@ -754,6 +757,7 @@ struct SoloHandle {
   SimConst sc;
   int n, njl, nj, A, D0, D, device, K, cap;
   int epw;   /* environments per warp of the step kernel (8, 4 or 2) */
+  int regs128;  /* SOLO_STEP_REGS=128: the 16-warps-per-SM build of the step kernel (large batches) */
   uint64_t seed;
   long long env_id_offset;
   float goal_radius;
@@ -789,16 +793,17 @@ static StepArgs make_step_args(SoloHandle* h, int mode, int n, const float* in, 
   a.force_settle = -1;
   return a;
 }
-template <int EPW>
+template <int EPW, int MINB>
 static void launch_step_epw(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
   const int blocks = (a.n + EPW - 1) / EPW;
-  if (h->njl == 3) step_kernel<3, EPW><<<blocks, kBlockThreads, 0, s>>>(a);
-  else step_kernel<2, EPW><<<blocks, kBlockThreads, 0, s>>>(a);
+  if (h->njl == 3) step_kernel<3, EPW, MINB><<<blocks, kBlockThreads, 0, s>>>(a);
+  else step_kernel<2, EPW, MINB><<<blocks, kBlockThreads, 0, s>>>(a);
 }
 static void launch_step(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
-  if (h->epw == 2) launch_step_epw<2>(h, a, s);
-  else if (h->epw == 4) launch_step_epw<4>(h, a, s);
-  else launch_step_epw<8>(h, a, s);
+  if (h->regs128) launch_step_epw<8, 16>(h, a, s);
+  else if (h->epw == 2) launch_step_epw<2, 1>(h, a, s);
+  else if (h->epw == 4) launch_step_epw<4, 1>(h, a, s);
+  else launch_step_epw<8, 1>(h, a, s);
   h->launches++;
 }
 /* Environments per warp.  Measured on B200 (profiles/r1_sweep_epw.txt): full warps win at every
@@ -892,6 +897,7 @@ int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_
   h->goal_radius = (float)params->goal_radius;
   h->was_reset = false; h->launches = 0;
   h->epw = choose_epw(num_envs, device);
+  { const char* ev = getenv("SOLO_STEP_REGS"); h->regs128 = (ev && atoi(ev) == 128); if (h->regs128) h->epw = 8; }
   h->K = params->settle_max - params->settle_min; if (h->K < 1) h->K = 1;
   h->cap = num_envs > h->K ? num_envs : h->K;
   h->s_act = h->s_obs = h->s_rew = h->s_done = nullptr;
