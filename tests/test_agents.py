@@ -187,3 +187,51 @@ def test_shipped_configs_keep_the_reference_keys(name, robot, task, control, H):
     p = params_from_config(cfg, m)
     assert m.name == robot and p.task == _TASK_NAMES[task] and p.control == _CONTROL_NAMES[control]
     assert p.num_history_stack == H and p.episode_length == 400
+
+
+def test_td3_replay_ring_batched_append_and_wrap():
+    from solorl_b200.agents.td3 import ReplayBuffer
+    rb = ReplayBuffer(10, 3, 2, "cpu")
+    for k in range(3):                                   # 3 x 4 transitions into a ring of 10: wraps once
+        o = torch.full((4, 3), float(k)) + torch.arange(4).reshape(4, 1) * 0.1
+        rb.append_batch(o, torch.zeros(4, 2), torch.full((4,), float(k)), o + 1, torch.ones(4))
+    assert len(rb) == 10 and rb._top == 2
+    assert torch.allclose(rb._observations[0], torch.full((3,), 2.2)) and torch.allclose(rb._observations[1], torch.full((3,), 2.3))
+    assert torch.allclose(rb._observations[2], torch.full((3,), 0.2))            # oldest surviving transition
+    assert torch.allclose(rb._next_observations[9], torch.full((3,), 3.1))
+    o, a, r, o2, nt = rb.sample(64)
+    assert o.shape == (64, 3) and a.shape == (64, 2) and r.shape == (64, 1) and nt.shape == (64, 1)
+    assert torch.allclose(o2, o + 1)                                             # rows stay aligned
+    rb2 = ReplayBuffer(5, 3, 2, "cpu")                                           # reference per-transition API
+    rb2.append([(torch.ones(3), torch.zeros(2), torch.tensor(1.0), torch.ones(3) * 2, torch.tensor(0.0))])
+    assert len(rb2) == 1 and float(rb2._not_terminal[0]) == 0.0
+
+
+def test_td3_models_keep_reference_layout_and_update_runs():
+    from solorl_b200.agents.td3 import TD3, ReplayBuffer
+    torch.manual_seed(0)
+    pol = TD3(10, 4, device="cpu")
+    assert sorted(pol.actor.state_dict()) == ["l1.bias", "l1.weight", "l2.bias", "l2.weight", "l3.bias", "l3.weight"]
+    assert pol.critic.l4.weight.shape == (256, 14) and pol.critic.l6.weight.shape == (1, 256)   # models.py:20-33
+    rb = ReplayBuffer(512, 10, 4, "cpu")
+    rb.append_batch(torch.randn(300, 10), torch.randn(300, 4).tanh(), torch.randn(300), torch.randn(300, 10),
+                    (torch.rand(300) > 0.1).float())
+    w0 = pol.actor.l3.weight.clone(); t0 = pol.actor_target.l3.weight.clone()
+    q, a = pol.train(rb, 1, 64)                      # odd step: critic only (policy_freq 2)
+    assert a is None and torch.equal(pol.actor.l3.weight, w0)
+    q, a = pol.train(rb, 2, 64)
+    assert a is not None and not torch.equal(pol.actor.l3.weight, w0)
+    # soft target update: target moved by tau towards the actor
+    assert torch.allclose(pol.actor_target.l3.weight, 0.995 * t0 + 0.005 * pol.actor.l3.weight, atol=1e-6)
+    assert (pol.select_action(torch.randn(5, 10)).abs() <= 1).all()
+
+
+def test_td3_cli_defaults_are_the_reference_defaults():
+    m = _load(os.path.join(ROOT, "training", "train_td3.py"))
+    a = m.get_td3_args([])
+    ref = dict(env_name="base", seed=0, start_timesteps=25e3, eval_freq=5e3, num_env_steps=1e6, expl_noise=0.1,
+               batch_size=256, gamma=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5, policy_freq=2, load_model="",
+               max_replay_size=1000000, num_agents=32, logdir=None, timestamp=None, log_interval=1000,
+               save_interval=2000, task=None)                                     # train_td3.py:10-39
+    for k, v in ref.items():
+        assert getattr(a, k) == v, k

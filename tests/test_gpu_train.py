@@ -90,3 +90,19 @@ def test_episode_return_statistics_of_trained_policy_within_5pct():
     assert abs(s["mean_length"] - length.mean()) <= 0.05 * length.mean()
     assert abs(np.percentile(gpu["episode_return"], 10) - np.percentile(ret, 10)) <= 0.05 * abs(ret.mean())
     assert abs(s["mean_reward"] - last.mean()) <= 0.05                     # last-step reward (what the reference prints)
+
+
+def test_td3_train_runs_on_the_vec_env(tmp_path):
+    from solorl_b200.agents import td3
+    cfg = make_config("solo8", "stand", "torque", 1, episode_length=30)
+    args = td3.default_args(num_agents=64, start_timesteps=64 * 20, num_env_steps=64 * 60, batch_size=128,
+                            log_interval=10, save_interval=20, logdir=str(tmp_path), max_replay_size=4096)
+    out = td3.train(args, cfg)
+    assert len(out["replay"]) == 64 * 60 and out["frames"] == 64 * 60
+    assert out["history"] and all(np.isfinite(h["q_loss"]) for h in out["history"])
+    ck = torch.load(os.path.join(tmp_path, "ckpt_final.pth"), weights_only=False)
+    assert set(ck) == {"update", "state_dict", "critic_state_dict"}          # agents/td3/train.py:142-154
+    # transitions stored by the ring are the env's: obs rows are finite, not_terminal is 0/1
+    assert torch.isfinite(out["replay"]._observations[:64 * 60]).all()
+    nt = out["replay"]._not_terminal[:64 * 60]
+    assert ((nt == 0) | (nt == 1)).all() and (nt == 0).any()
