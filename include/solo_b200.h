@@ -226,6 +226,18 @@ int solo_substep(SoloHandle* h, const float* d_tau, void* stream);
  * handle's current state. d_tau [N, nj]. */
 int solo_action_to_torque(SoloHandle* h, const float* d_actions, float* d_tau, void* stream);
 
+/* Gait envs: n_ticks simulator ticks under the joint-level PD + feed-forward actuator
+ * that the external PyBulletSimulator exposes to baseControlEnv.py:256-270
+ * (SetDesiredJointPDgains / Position / Velocity / Torque + SendCommand):
+ *   tau = clip(P (q_des - q) + D (v_des - v) + tau_ff, +-max_torque), recomputed before every tick,
+ * then one Bullet-equivalent step at params.dt (create the handle with dt = 0.002, the gait envs' tick).
+ * d_cmd float[N, 5, nj] = q_des, v_des, P, D, tau_ff.  State is read back with solo_get_state. */
+int solo_actuator_step(SoloHandle* h, const float* d_cmd, int32_t n_ticks, void* stream);
+
+/* World-frame centres of the four foot collision spheres, d_out float[N, 4, 3]
+ * (replaces get_feet_positions, baseControlEnv.py:410-414). */
+int solo_get_feet(SoloHandle* h, float* d_out, void* stream);
+
 /* Episode records of the last step (see SoloEpisodeStats). d_stats: SoloEpisodeStats[N]. */
 int solo_episode_stats(SoloHandle* h, SoloEpisodeStats* d_stats, void* stream);
 

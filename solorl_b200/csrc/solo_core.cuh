@@ -687,6 +687,48 @@ SOLO_HD void impulse_leg(Lane<NJL>& ln, const SimConst& sc, const float* lam3, c
   }
 }
 
+/* Forward kinematics of one leg: centre of the foot collision sphere in base coordinates
+ * (the kinematic part of leg_inward, for the feet-position query of the gait envs). */
+template <int NJL>
+SOLO_HD void leg_foot_center(const LegConst& lc, const float* q, float* out) {
+  float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+  float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    float r[3];
+    mat3_mulv(R, lc.jo[k], r);
+    o[0] += r[0]; o[1] += r[1]; o[2] += r[2];
+    float sn, cs;
+    solo_sincos(q[k], &sn, &cs);
+    if (axis_of<NJL>(k) == 0) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float c1 = R[3 * i + 1], c2 = R[3 * i + 2];
+        R[3 * i + 1] = cs * c1 + sn * c2;
+        R[3 * i + 2] = cs * c2 - sn * c1;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float c0 = R[3 * i + 0], c2 = R[3 * i + 2];
+        R[3 * i + 0] = cs * c0 - sn * c2;
+        R[3 * i + 2] = sn * c0 + cs * c2;
+      }
+    }
+  }
+  float f[3];
+  mat3_mulv(R, lc.foot_ctr, f);
+  out[0] = o[0] + f[0]; out[1] = o[1] + f[1]; out[2] = o[2] + f[2];
+}
+
+/* Joint-level PD + feed-forward actuator of the gait envs' simulator ([3P] PyBulletSimulator.SendCommand
+ * of LAAS quadruped-reactive-walking, the surface baseControlEnv.py:256-270 drives):
+ * tau = P (q_des - q) + D (v_des - v) + tau_ff, saturated at the motor limit. */
+SOLO_HD float actuator_torque(const SimConst& sc, float q, float qd, float q_des, float v_des, float P, float D,
+                              float tau_ff) {
+  return clampf(P * (q_des - q) + D * (v_des - qd) + tau_ff, -sc.max_torque, sc.max_torque);
+}
+
 /* Semi-implicit Euler position update ([3P] btMultiBody::stepPositionsMultiDof). */
 SOLO_HD void integrate_base(const SimConst& sc, BaseState& s) {
 #pragma unroll

@@ -513,6 +513,80 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) step_kernel(const __grid_
   }
 }
 
+/* n_ticks simulator ticks under the joint-level PD + feed-forward actuator: the
+ * torque is recomputed from the current joint state before every tick, as the external simulator's
+ * SendCommand does once per control tick (baseControlEnv.py:256-270).  cmd [n][5][nj] = q_des, v_des,
+ * P, D, tau_ff.  No env bookkeeping: the gait-env shell on top owns reward / termination. */
+template <int NJL>
+__global__ void __launch_bounds__(kBlockThreads) actuator_kernel(const __grid_constant__ StepArgs args, int n_ticks) {
+  __shared__ Smem sm;
+  const int tid = threadIdx.x;
+  const SimConst& sc = args.sc;
+  {
+    const float* src = reinterpret_cast<const float*>(&args.mc.leg[0]);
+    float* dst = reinterpret_cast<float*>(&sm.leg[0]);
+    for (int i = tid; i < (int)(sizeof(LegConst) * 4 / sizeof(float)); i += kBlockThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  const DevArrays& d = args.d;
+  const int el = tid >> 2, leg = tid & 3;
+  const int env = blockIdx.x * 8 + el;
+  const bool valid = env < args.n;
+  const int e = valid ? env : args.n - 1;
+  BaseState st;
+  float goal[2], potential;
+  load_base(d.base, e, st, goal, potential);
+  Lane<NJL> ln;
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    ln.q[k] = d.q[((size_t)k * d.cap + e) * 4 + leg];
+    ln.qd[k] = d.qd[((size_t)k * d.cap + e) * 4 + leg];
+  }
+  float cforce = d.cforce[e * 4 + leg];
+  const int nj = 4 * NJL;
+  const float* c = args.in + (size_t)e * 5 * nj + leg * NJL;
+  float qdes[NJL], vdes[NJL], P[NJL], D[NJL], tff[NJL];
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    qdes[k] = c[k]; vdes[k] = c[nj + k]; P[k] = c[2 * nj + k]; D[k] = c[3 * nj + k]; tff[k] = c[4 * nj + k];
+  }
+  int nc_sum = 0, sweep_feet = 0;
+  for (int s = 0; s < n_ticks; s++) {
+    float tau[NJL];
+#pragma unroll
+    for (int k = 0; k < NJL; k++) tau[k] = actuator_torque(sc, ln.q[k], ln.qd[k], qdes[k], vdes[k], P[k], D[k], tff[k]);
+    group_substep<NJL>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet);
+  }
+  if (valid) {
+    if (leg == 0) store_base(d.base, e, st, goal, potential);
+#pragma unroll
+    for (int k = 0; k < NJL; k++) {
+      d.q[((size_t)k * d.cap + e) * 4 + leg] = ln.q[k];
+      d.qd[((size_t)k * d.cap + e) * 4 + leg] = ln.qd[k];
+    }
+    d.cforce[e * 4 + leg] = cforce;
+  }
+}
+
+/* world-frame centres of the four foot collision spheres, out [n][4][3] */
+template <int NJL>
+__global__ void feet_kernel(DevArrays d, ModelConst mc, int n, float* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t >> 2, leg = t & 3;
+  if (e >= n) return;
+  BaseState st;
+  float goal[2], potential;
+  load_base(d.base, e, st, goal, potential);
+  float q[NJL], fb[3], fw[3], R[9];
+#pragma unroll
+  for (int k = 0; k < NJL; k++) q[k] = d.q[((size_t)k * d.cap + e) * 4 + leg];
+  leg_foot_center<NJL>(mc.leg[leg], q, fb);
+  quat_to_rot(st.q, R);
+  mat3_mulv(R, fb, fw);
+  float* o = out + ((size_t)e * 4 + leg) * 3;
+  o[0] = st.p[0] + fw[0]; o[1] = st.p[1] + fw[1]; o[2] = st.p[2] + fw[2];
+}
+
 /* VecEnvWrapper.reset (agents/ppo/envs.py:97-100): masked begin_reset, four lanes per env */
 template <int NJL>
 __global__ void reset_kernel(const __grid_constant__ ResetArgs args) {
@@ -1077,6 +1151,30 @@ int solo_substep(SoloHandle* h, const float* d_tau, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   StepArgs a = make_step_args(h, MODE_SUBSTEP, h->n, d_tau, nullptr, nullptr, nullptr);
   launch_step(h, a, s);
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_actuator_step(SoloHandle* h, const float* d_cmd, int32_t n_ticks, void* stream) {
+  if (!h || !d_cmd || n_ticks <= 0) return fail(h, SOLO_E_ARG, "bad argument to solo_actuator_step");
+  if (!h->was_reset) return fail(h, SOLO_E_STATE, "env.reset() must be called before step");
+  cudaStream_t s = (cudaStream_t)stream;
+  StepArgs a = make_step_args(h, MODE_SUBSTEP, h->n, d_cmd, nullptr, nullptr, nullptr);
+  const int blocks = (h->n + 7) / 8;
+  if (h->njl == 3) actuator_kernel<3><<<blocks, kBlockThreads, 0, s>>>(a, n_ticks);
+  else actuator_kernel<2><<<blocks, kBlockThreads, 0, s>>>(a, n_ticks);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_get_feet(SoloHandle* h, float* d_out, void* stream) {
+  if (!h || !d_out) return fail(h, SOLO_E_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int threads = 128, blocks = (h->n * 4 + threads - 1) / threads;
+  if (h->njl == 3) feet_kernel<3><<<blocks, threads, 0, s>>>(h->d, h->mc, h->n, d_out);
+  else feet_kernel<2><<<blocks, threads, 0, s>>>(h->d, h->mc, h->n, d_out);
+  h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return SOLO_OK;
 }

@@ -270,14 +270,19 @@ class SoloBaseEnv:
 def make_vec_envs(config, num_envs, env_constructor=SoloBaseEnv, gamma=0.99,
                   device: Optional[torch.device] = None, training=True, seed: int = 0,
                   env_id_offset: int = 0):
-    """``agents/ppo/envs.py:14-30`` with the same signature.  ``env_constructor`` must be
-    :class:`SoloBaseEnv` (the other reference env classes wrap an external MPC controller
-    that is not part of the reference tree)."""
-    if env_constructor is not SoloBaseEnv and getattr(env_constructor, "__name__", "") != "SoloBaseEnv":
-        raise NotImplementedError(f"env_constructor {env_constructor!r}: only SoloBaseEnv is built")
+    """``agents/ppo/envs.py:14-30`` with the same signature.  ``env_constructor`` is
+    :class:`SoloBaseEnv` or :class:`solorl_b200.gait.SoloGaitEnvContact` (the env shell with a pluggable
+    controller; the other reference env classes cannot be constructed from any shipped config)."""
+    name = getattr(env_constructor, "__name__", "")
+    if name not in ("SoloBaseEnv", "SoloGaitEnvContact"):
+        raise NotImplementedError(f"env_constructor {env_constructor!r}: SoloBaseEnv and SoloGaitEnvContact are built")
     if device is None or torch.device(device).type != "cuda":
         device = torch.device("cuda", torch.cuda.current_device())
-    envs = SoloVecEnv(config, num_envs, device=device, seed=seed, env_id_offset=env_id_offset)
+    if name == "SoloGaitEnvContact":
+        from .gait import SoloGaitVecEnv
+        envs = SoloGaitVecEnv(config, num_envs, device=device, seed=seed)
+    else:
+        envs = SoloVecEnv(config, num_envs, device=device, seed=seed, env_id_offset=env_id_offset)
     envs = VecNormalize(envs, ob=False, ret=False, clipob=100, cliprew=100, gamma=gamma)
     if not training:
         envs.eval()

@@ -143,6 +143,17 @@ class SoloSim:
         _lib.check(self.L.solo_action_to_torque(self.h, _ptr(a), _ptr(out), self._stream()), self.h)
         return out
 
+    # ---- gait-env actuator interface ------------------------------------
+    def actuator_step(self, cmd, n_ticks=1):
+        """cmd [N,5,nj] = q_des, v_des, P, D, tau_ff; n_ticks simulator ticks at params.dt."""
+        c = self._f32(cmd, (self.n, 5, self.nj))
+        _lib.check(self.L.solo_actuator_step(self.h, _ptr(c), int(n_ticks), self._stream()), self.h)
+
+    def get_feet(self):
+        out = torch.empty(self.n, 4, 3, dtype=torch.float32, device=self.device)
+        _lib.check(self.L.solo_get_feet(self.h, _ptr(out), self._stream()), self.h)
+        return out
+
     @property
     def launch_count(self):
         return int(self.L.solo_launch_count(self.h))

@@ -1,0 +1,132 @@
+"""GPU tests of the gait-env row: actuator tick against the oracle, feet
+positions, and the SoloGaitEnvContact shell arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import stance_states
+
+pytestmark = pytest.mark.gpu
+
+
+def _actuator(n, seed=0):
+    from solorl_b200.gait import ActuatorSim
+    return ActuatorSim(n, solo12=True, dt=0.002, device=0, seed=seed)
+
+
+def test_actuator_tick_matches_oracle_1e3():
+    """tau = clip(P (q_des - q) + D (v_des - v) + tau_ff, +-3) then one 0.002 s simulator tick:
+    GPU vs (numpy torque law -> oracle substep); 1e-3 like the contact substep (north_star)."""
+    from oracle.oracle import OracleEnv
+    rng = np.random.default_rng(3)
+    n, nj = 64, 12
+    rob = _actuator(n)
+    s0 = stance_states(rng, n, nj, z=0.24, noise=0.1)
+    rob.sim.set_state(torch.from_numpy(s0.astype(np.float32)).cuda())
+    cmd = np.zeros((n, 5, nj), np.float32)
+    cmd[:, 0] = s0[:, 13:13 + nj] + rng.normal(size=(n, nj)) * 0.3
+    cmd[:, 1] = rng.normal(size=(n, nj))
+    cmd[:, 2] = rng.uniform(0, 6, size=(n, nj))
+    cmd[:, 3] = rng.uniform(0, 0.3, size=(n, nj))
+    cmd[:, 4] = rng.uniform(-1, 1, size=(n, nj))
+    ticks = 5
+    rob.sim.actuator_step(torch.from_numpy(cmd).cuda(), ticks)
+    got = rob.sim.get_state().cpu().numpy()
+    feet = rob.sim.get_feet().cpu().numpy()
+    worst = worst_feet = 0.0
+    contacts = 0
+    for i in range(0, n, 4):
+        o = OracleEnv(rob.model, rob.params)
+        o.set_state(s0[i])
+        for _ in range(ticks):
+            s = o.get_state()
+            q, qd = s[13:13 + nj], s[13 + nj:]
+            c = cmd[i].astype(np.float64)
+            tau = np.clip(c[2] * (c[0] - q) + c[3] * (c[1] - qd) + c[4], -3.0, 3.0)
+            o.substep(tau)
+        ref = o.get_state()
+        contacts += int(o.get_contacts()[:, 1].sum())
+        worst = max(worst, float((np.abs(ref - got[i]) / np.maximum(1.0, np.abs(ref))).max()))
+        worst_feet = max(worst_feet, float(np.abs(o.foot_positions() - feet[i]).max()))
+    assert contacts > 0
+    assert worst < 1e-3, worst
+    assert worst_feet < 1e-3, worst_feet
+
+
+def test_feet_positions_match_oracle_1e5():
+    from oracle.oracle import OracleEnv
+    from tests.helpers import random_states
+    rng = np.random.default_rng(4)
+    n = 32
+    rob = _actuator(n)
+    s = random_states(rng, n, 12)
+    rob.sim.set_state(torch.from_numpy(s.astype(np.float32)).cuda())
+    feet = rob.sim.get_feet().cpu().numpy()
+    o = OracleEnv(rob.model, rob.params)
+    for i in range(n):
+        o.set_state(s[i])
+        assert np.abs(o.foot_positions() - feet[i]).max() < 1e-5
+
+
+def test_gait_shell_observation_reward_and_termination():
+    from solorl_b200.gait import GAIT_TABLE, SoloGaitVecEnv, Q_INIT
+    cfg = {"solo12": True, "episode_length": 3, "vel_switch": 1000, "mode": "headless", "num_history_stack": 1,
+           "flat_ground": True, "auto_vel_switch": True}
+    n = 16
+    env = SoloGaitVecEnv(cfg, n, seed=1)
+    assert env.k_rl == 80 and env.observation_space.shape == (64,) and env.action_space.n == 9
+    with pytest.raises(AssertionError):
+        env.step(torch.zeros(n, dtype=torch.long))                        # baseControlEnv.py:135
+    obs = env.reset()
+    assert obs.shape == (n, 64)
+    o = obs.cpu().numpy()
+    assert np.allclose(o[:, 0], env.robot.z_init, atol=1e-6) and np.allclose(o[:, 1:4], 0, atol=1e-6)
+    assert np.allclose(o[:, 10:22], np.array(Q_INIT), atol=1e-6) and np.allclose(o[:, 22:34], 0)
+    assert np.allclose(o[:, 46:58], 0) and np.allclose(o[:, 58:64], 0)    # past gaits = -1 -> zeros; v_ref masked to 0
+    feet_z = o[:, 34:46].reshape(n, 4, 3)[:, :, 2]
+    assert np.allclose(feet_z.min(axis=1), env.robot.model.foot_radius, atol=1e-5)
+    a = torch.tensor([0, 5, 7, 8] * 4)
+    for t in range(3):
+        obs, rew, done, infos = env.step(a)
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and (rew <= 1.0 + 1e-6).all()
+        if t < 2:
+            seq = obs[:, 46:58].reshape(n, 3, 4)
+            assert torch.allclose(seq[:, 2].cpu(), torch.tensor(GAIT_TABLE)[a])    # newest pattern last
+    assert done.sum().item() >= 1
+    i = int(torch.nonzero(done)[0])
+    info = infos[i]
+    assert info["episode_length"] <= 3 and set(["success", "timeout", "dr/Energy_pen", "dr/body_velocity"]) <= set(info)
+    # an env that timed out at exactly episode_length is a success (baseControlEnv.py:186)
+    to = [k for k in range(n) if done[k] > 0.5 and infos[k]["timeout"]]
+    assert all(infos[k]["success"] and infos[k]["episode_length"] == 3 for k in to)
+    assert (env.timestep[done > 0.5] == 0).all()                          # auto-reset
+    env.close()
+
+
+def test_posture_controller_keeps_the_robot_up_and_power_model():
+    from solorl_b200.gait import COULOMB_TAU, K_MOTOR, VISCOUS_B, SoloGaitVecEnv
+    cfg = {"solo12": True, "episode_length": 50, "mode": "headless", "flat_ground": True, "auto_vel_switch": True}
+    env = SoloGaitVecEnv(cfg, 8, seed=2)
+    env.reset()
+    for t in range(10):
+        obs, rew, done, infos = env.step(torch.zeros(8, dtype=torch.long))          # "Static": all feet in stance
+    assert (obs[:, 0] > 0.15).all() and done.sum().item() == 0
+    assert (rew > 0.5).all()                                                        # small energy, zero velocity error
+    qd = env.robot.v_mes.cpu().numpy().astype(np.float64)
+    tau = env.robot.tau_ff.cpu().numpy().astype(np.float64)
+    ref = (COULOMB_TAU * np.sign(qd) + VISCOUS_B * qd) * qd + K_MOTOR * tau ** 2     # baseControlEnv.py:436-445
+    assert np.abs(env.get_joints_power().cpu().numpy() - ref).max() < 1e-6
+    env.close()
+
+
+def test_make_vec_envs_accepts_the_contact_env():
+    from solorl_b200.envs import make_vec_envs
+    from solorl_b200.gait import SoloGaitEnvContact
+    import yaml, os
+    from tests.helpers import ROOT
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "basic_contact.yaml")))
+    envs = make_vec_envs(cfg, 4, SoloGaitEnvContact)
+    obs = envs.reset()
+    obs, rew, done, infos = envs.step(torch.tensor([1, 2, 3, 4]))
+    assert obs.shape == (4, 64) and rew.shape == (4, 1) and done.shape == (4,)
+    envs.close()
