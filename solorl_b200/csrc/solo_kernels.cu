@@ -257,6 +257,60 @@ __device__ __forceinline__ void begin_reset(const DevArrays& d, const SimConst& 
   potential = (sc.task == 2) ? calc_potential(st, goal) : 0.f;   /* solo.py:176 */
 }
 
+/* The projected Gauss-Seidel sweep loop of one env over its four lanes (PgsLane: each lane owns the
+ * three rows of its foot).  Per row relaxation: the owner's candidate, ONE shuffle broadcast of the
+ * impulse change inside the 4-lane group, three FMAs in every lane.  An env whose sweep met Bullet's
+ * residual test keeps relaxing until the whole warp is done (no per-row select on the dependent chain);
+ * its impulses are latched into lam3 at the sweep that converged, so the result is exactly that of
+ * stopping there.  CONE selects Bullet's implicit-cone friction rows or the pyramid ones. */
+template <bool CONE>
+__device__ __forceinline__ void pgs_sweeps(PgsLane& pl, const SimConst& sc, int leg, unsigned gbase, unsigned amask,
+                                           int nc, float* lam3, int& sweep_feet) {
+  const unsigned kFull = 0xffffffffu;
+  bool conv = (amask == 0);          /* env-uniform: the sweep loop of this env has ended */
+  lam3[0] = lam3[1] = lam3[2] = 0.f;
+  for (int it = 0; it < sc.iters; it++) {
+    float res_own = 0.f;             /* largest |velocity residual| among the rows this lane relaxed */
+    sweep_feet += conv ? 0 : nc;
+#pragma unroll
+    for (int f = 0; f < 4; f++) {   /* feet without contact hold zero rows: no skip branches */
+      float nv, d, rv;
+      pgs_normal_candidate(pl, nv, d, rv);
+      const float db = __shfl_sync(kFull, d, gbase + f);
+      if (leg == f) { pl.lam[0] = nv; res_own = fmaxf(res_own, fabsf(rv)); }
+      pgs_apply(pl, row_of(f, 0), db);
+    }
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      if (CONE) {
+        float nA, nB, dA, dB, rv;
+        pgs_cone_candidate(pl, sc.mu, nA, nB, dA, dB, rv);
+        const float dAb = __shfl_sync(kFull, dA, gbase + f);
+        const float dBb = __shfl_sync(kFull, dB, gbase + f);
+        if (leg == f) { pl.lam[1] = nA; pl.lam[2] = nB; res_own = fmaxf(res_own, fabsf(rv)); }
+        pgs_apply(pl, row_of(f, 1), dAb);
+        pgs_apply(pl, row_of(f, 2), dBb);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          float nv, d, rv;
+          pgs_pyramid_candidate(pl, sc.mu, q, nv, d, rv);
+          const float db = __shfl_sync(kFull, d, gbase + f);
+          if (leg == f) { pl.lam[1 + q] = nv; res_own = fmaxf(res_own, fabsf(rv)); }
+          pgs_apply(pl, row_of(f, 1 + q), db);
+        }
+      }
+    }
+    if (!conv) { lam3[0] = pl.lam[0]; lam3[1] = pl.lam[1]; lam3[2] = pl.lam[2]; }
+    /* end of sweep, Bullet's exit test: the env is done when every row residual of the sweep is
+     * within the threshold, i.e. when each of its four lanes is; one ballot serves the env test
+     * and the warp-wide loop exit */
+    const unsigned okb = __ballot_sync(kFull, conv || (res_own * res_own <= sc.res_thr));
+    conv = conv || (((okb >> gbase) & 0xFu) == 0xFu);
+    if (okb == kFull) break;
+  }
+}
+
 /* One Bullet-equivalent substep for the four lanes of an env (see solo_core.cuh).
  * Control flow is kept WARP-uniform (skip masks and the sweep-loop exit are warp votes, envs that
  * have nothing to do contribute exact zeros) so that every shuffle is a full-mask shuffle of a
@@ -309,52 +363,8 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
     }
     const int nc = __popc(amask);
     nc_sum += nc;
-    bool conv = (amask == 0);          /* env-uniform: the sweep loop of this env has ended */
-    for (int it = 0; it < sc.iters; it++) {
-      float res_own = 0.f;             /* largest |velocity residual| among the rows this lane relaxed */
-      sweep_feet += conv ? 0 : nc;
-#pragma unroll
-      for (int f = 0; f < 4; f++) {   /* feet without contact hold zero rows: no skip branches */
-        float nv, d, rv;
-        pgs_normal_candidate(pl, nv, d, rv);
-        d = conv ? 0.f : d;
-        const float db = __shfl_sync(kFull, d, gbase + f);
-        if (leg == f && !conv) { pl.lam[0] = nv; res_own = fmaxf(res_own, fabsf(rv)); }
-        pgs_apply(pl, row_of(f, 0), db);
-      }
-#pragma unroll
-      for (int f = 0; f < 4; f++) {
-        if (sc.cone) {
-          float nA, nB, dA, dB, rv;
-          pgs_cone_candidate(pl, sc.mu, nA, nB, dA, dB, rv);
-          dA = conv ? 0.f : dA;
-          dB = conv ? 0.f : dB;
-          const float dAb = __shfl_sync(kFull, dA, gbase + f);
-          const float dBb = __shfl_sync(kFull, dB, gbase + f);
-          if (leg == f && !conv) { pl.lam[1] = nA; pl.lam[2] = nB; res_own = fmaxf(res_own, fabsf(rv)); }
-          pgs_apply(pl, row_of(f, 1), dAb);
-          pgs_apply(pl, row_of(f, 2), dBb);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 2; q++) {
-            float nv, d, rv;
-            pgs_pyramid_candidate(pl, sc.mu, q, nv, d, rv);
-            d = conv ? 0.f : d;
-            const float db = __shfl_sync(kFull, d, gbase + f);
-            if (leg == f && !conv) { pl.lam[1 + q] = nv; res_own = fmaxf(res_own, fabsf(rv)); }
-            pgs_apply(pl, row_of(f, 1 + q), db);
-          }
-        }
-      }
-      /* end of sweep, Bullet's exit test: the env is done when every row residual of the sweep is
-       * within the threshold, i.e. when each of its four lanes is; one ballot serves the env test
-       * and the warp-wide loop exit */
-      const unsigned okb = __ballot_sync(kFull, conv || (res_own * res_own <= sc.res_thr));
-      conv = conv || (((okb >> gbase) & 0xFu) == 0xFu);
-      if (okb == kFull) break;
-    }
-#pragma unroll
-    for (int m = 0; m < 3; m++) lam3[m] = pl.lam[m];
+    if (sc.cone) pgs_sweeps<true>(pl, sc, leg, gbase, amask, nc, lam3, sweep_feet);
+    else pgs_sweeps<false>(pl, sc, leg, gbase, amask, nc, lam3, sweep_feet);
     float part[6], dv0[6];
     impulse_base_part<NJL>(ln, lam3, part);
 #pragma unroll

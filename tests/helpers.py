@@ -56,6 +56,11 @@ def euler_slots(d0, blocks):
     return np.array(idx)
 
 
+def flag_slots(d0, nj, blocks):
+    """Indices of the four foot-contact flags of every D0 block of an observation (solo.py:219-220)."""
+    return np.array([b * d0 + 10 + 2 * nj + k for b in range(blocks) for k in range(4)])
+
+
 def obs_diff(a, b, d0):
     """|a - b| with the three Euler slots of every D0 block compared modulo 1: the reference's
     observation maps an Euler angle e to (e mod 2)/2 (solo.py:206), which jumps by 1

@@ -12,7 +12,7 @@ from oracle import oracle as orc
 from oracle.oracle import OracleEnv
 from solorl_b200.abi import params_from_config
 from solorl_b200.model import SoloModel
-from tests.helpers import GOLDEN, make_config, obs_diff, random_states, stance_states
+from tests.helpers import flag_slots, GOLDEN, make_config, obs_diff, random_states, stance_states
 
 pytestmark = pytest.mark.gpu
 
@@ -215,6 +215,10 @@ def test_env_rollout_with_reset(robot, task, control, H):
     for i, o in enumerate(ors):
         assert obs_diff(o.reset(), obs[i], o.d0).max() < 5e-4
     episodes = 0
+    # the contact flag is a threshold test (normal force < 0.2 N): on free-running trajectories a
+    # force within float noise of the threshold flips it, so flags are counted instead of bounded
+    fl = flag_slots(ors[0].d0, env.sim.nj, 1 + H)
+    flag_cmp = flag_bad = 0
     for t in range(30):
         a = rng.uniform(-1.2, 1.2, size=(n, env.sim.act_dim)).astype(np.float32)
         ob, rw, dn, infos = env.step(torch.from_numpy(a).cuda())
@@ -222,7 +226,15 @@ def test_env_rollout_with_reset(robot, task, control, H):
         for i, o in enumerate(ors):
             oo, r, d, info = o.step(a[i].astype(np.float64), auto_reset=True)
             assert d == (dn[i] > 0.5)
-            assert obs_diff(oo, ob[i], o.d0).max() < 2e-2   # free-running trajectories: glue logic, not numerics
+            df = obs_diff(oo, ob[i], o.d0)
+            flag_cmp += len(fl); flag_bad += int((df[fl] > 0.5).sum())
+            df[fl] = 0.0
+            # free-running trajectories (up to 12 env steps of contact dynamics without re-injection):
+            # glue logic, not numerics.  fp32-vs-fp64 differences grow ~10x per 4 env steps through the contact
+            # events of a flailing robot (tools/dbg_rollout.py: 1e-5 after one step, up to 3e-2 on the
+            # angular velocity after 11), so the bound is 10 % of the slot's magnitude; the per-step numerics
+            # are bounded by the 1e-5 / 1e-6 / 1e-3 tests above
+            assert (df / np.maximum(1.0, np.abs(oo))).max() < 1e-1
             assert abs(r - rw[i]) < 2e-2 * max(1.0, abs(r))
             if d:
                 episodes += 1
@@ -237,6 +249,7 @@ def test_env_rollout_with_reset(robot, task, control, H):
             else:
                 assert infos[i] == {}
     assert episodes >= nref * 2
+    assert flag_bad <= 0.01 * flag_cmp, (flag_bad, flag_cmp)
     env.close()
 
 
