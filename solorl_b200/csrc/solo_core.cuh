@@ -259,29 +259,41 @@ struct Ldl6 {
   float L[15];   /* strictly lower, row-major: (1,0) (2,0) (2,1) (3,0) ... (5,4) */
   float dinv[6];
 };
-SOLO_HD int ldl_idx(int i, int j) { return i * (i - 1) / 2 + j; }
+SOLO_HD constexpr int ldl_idx(int i, int j) { return i * (i - 1) / 2 + j; }
+/* column J of the factorisation; J is a template constant so that every loop has a constant trip
+ * count and all indices fold: the factor lives in registers (a run-time j left L, d and the 6x6 copy
+ * in local memory, with LDL/STL round trips on the dependent chain) */
+template <int J>
+SOLO_HD void ldl6_column(const float (&a)[6][6], Ldl6& F, float (&d)[6]) {
+  float s = a[J][J];
+#pragma unroll
+  for (int k = 0; k < J; k++) s -= F.L[ldl_idx(J, k)] * F.L[ldl_idx(J, k)] * d[k];
+  d[J] = s;
+  F.dinv[J] = solo_rcp(s);
+#pragma unroll
+  for (int i = J + 1; i < 6; i++) {
+    float t = a[i][J];
+#pragma unroll
+    for (int k = 0; k < J; k++) t -= F.L[ldl_idx(i, k)] * F.L[ldl_idx(J, k)] * d[k];
+    F.L[ldl_idx(i, J)] = t * F.dinv[J];
+  }
+}
 SOLO_HD void ldl6_factor(const Sym6& I, Ldl6& F) {
   float a[6][6];
   a[0][0] = I.A[0]; a[1][0] = I.A[1]; a[2][0] = I.A[2]; a[1][1] = I.A[3]; a[2][1] = I.A[4]; a[2][2] = I.A[5];
-  for (int i = 0; i < 3; i++)
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
     for (int j = 0; j < 3; j++) a[3 + i][j] = I.H[3 * j + i]; /* lower-left block = H^T */
+  }
   a[3][3] = I.M[0]; a[4][3] = I.M[1]; a[5][3] = I.M[2]; a[4][4] = I.M[3]; a[5][4] = I.M[4]; a[5][5] = I.M[5];
   float d[6];
-#pragma unroll
-  for (int j = 0; j < 6; j++) {
-    float s = a[j][j];
-#pragma unroll
-    for (int k = 0; k < j; k++) s -= F.L[ldl_idx(j, k)] * F.L[ldl_idx(j, k)] * d[k];
-    d[j] = s;
-    F.dinv[j] = solo_rcp(s);
-#pragma unroll
-    for (int i = j + 1; i < 6; i++) {
-      float t = a[i][j];
-#pragma unroll
-      for (int k = 0; k < j; k++) t -= F.L[ldl_idx(i, k)] * F.L[ldl_idx(j, k)] * d[k];
-      F.L[ldl_idx(i, j)] = t * F.dinv[j];
-    }
-  }
+  ldl6_column<0>(a, F, d);
+  ldl6_column<1>(a, F, d);
+  ldl6_column<2>(a, F, d);
+  ldl6_column<3>(a, F, d);
+  ldl6_column<4>(a, F, d);
+  ldl6_column<5>(a, F, d);
 }
 SOLO_HD void ldl6_solve(const Ldl6& F, float* x) { /* in place */
 #pragma unroll
@@ -607,12 +619,16 @@ SOLO_HD constexpr int row_of(int foot, int m) { return m == 0 ? foot : 4 + 2 * f
 /* Rows of the scaled Delassus matrix owned by one foot, built one column block at a time:
  *   A = P^T IA0^-1 P + blockdiag(L),  B[m][c] = A[r_m][c] / A[r_m][r_m],  g0[m] = b[m] / A[r_m][r_m].
  * assemble_block adds the 3x3 block against foot j (Kj = K of foot j, fetched from that lane). */
+SOLO_HD constexpr int sym3_idx(int m, int n) { return m == n ? (m == 0 ? 0 : (m == 1 ? 3 : 5)) : (m + n == 1 ? 1 : (m + n == 2 ? 2 : 4)); }
+/* `foot` (this lane's leg) is a run-time value and j a compile-time one: the own-foot block is picked
+ * with selects, never by indexing `rows` with `foot`, so the rows stay in registers. */
 template <int NJL>
-SOLO_HD void assemble_block(const Lane<NJL>& ln, int j, const float Kj[3][6], float rows[3][kRows]) {
+SOLO_HD void assemble_block(const Lane<NJL>& ln, int foot, int j, const float Kj[3][6], float rows[3][kRows]) {
+  const bool own = (j == foot);
 #pragma unroll
   for (int m = 0; m < 3; m++) {
 #pragma unroll
-    for (int n = 0; n < 3; n++) rows[m][row_of(j, n)] = dot6(ln.P[m], Kj[n]);
+    for (int n = 0; n < 3; n++) rows[m][row_of(j, n)] = dot6(ln.P[m], Kj[n]) + (own ? ln.Lm[sym3_idx(m, n)] : 0.f);
   }
 }
 
@@ -634,13 +650,11 @@ struct PgsLane {
 template <int NJL>
 SOLO_HD void pgs_lane_init(const Lane<NJL>& ln, int foot, float rows[3][kRows], unsigned active_mask,
                            PgsLane& pl) {
-  const int lidx[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
 #pragma unroll
   for (int m = 0; m < 3; m++) {
-    const int r = row_of(foot, m);
+    float d = 1.0f;
 #pragma unroll
-    for (int n = 0; n < 3; n++) rows[m][row_of(foot, n)] += ln.Lm[lidx[m][n]];
-    const float d = rows[m][r];
+    for (int j = 0; j < 4; j++) d = (j == foot) ? rows[m][row_of(j, m)] : d;
     const float invd = ln.active ? solo_rcp(d) : 0.f;
     pl.diag[m] = ln.active ? d : 0.f;
 #pragma unroll
@@ -648,7 +662,8 @@ SOLO_HD void pgs_lane_init(const Lane<NJL>& ln, int foot, float rows[3][kRows], 
 #pragma unroll
       for (int n = 0; n < 3; n++) {
         const int c = row_of(j, n);
-        pl.B[m][c] = (((active_mask >> j) & 1u) && c != r) ? rows[m][c] * invd : 0.f;
+        const bool own_diag = (j == foot) && (n == m);
+        pl.B[m][c] = (((active_mask >> j) & 1u) && !own_diag) ? rows[m][c] * invd : 0.f;
       }
     }
     pl.g[m] = ln.b[m] * invd;

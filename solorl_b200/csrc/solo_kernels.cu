@@ -357,7 +357,7 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
 #pragma unroll
           for (int i = 0; i < 6; i++) Kj[n][i] = __shfl_sync(kFull, ln.K[n][i], gbase + j);
         }
-        assemble_block<NJL>(ln, j, Kj, rows);
+        assemble_block<NJL>(ln, leg, j, Kj, rows);
       }
       pgs_lane_init<NJL>(ln, leg, rows, amask, pl);
     }
@@ -381,29 +381,35 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
   for (int k = 0; k < NJL; k++) ln.q[k] += sc.dt * ln.qd[k];
 }
 
-/* MINB = minimum resident blocks per SM asked of the compiler: 1 lets it use 255 registers (8 warps
- * per SM: shortest per-warp chain, best below ~8k envs), 16 caps it at 128 registers (16 warps per SM,
- * some spills: +18 % throughput once several waves are resident, profiles/r1_sweep_regs.txt).
- * EPW = environments per warp (8, 4 or 2).  Below ~2 warps per scheduler the step is latency-bound,
- * so small batches spread over MORE warps: with EPW < 8 the lanes past 4*EPW mirror the first ones
- * (same env, same arithmetic, no stores), which keeps every warp vote and shuffle unchanged. */
-template <int NJL, int EPW, int MINB>
-__global__ void __launch_bounds__(kBlockThreads, MINB) step_kernel(const __grid_constant__ StepArgs args) {
+/* Two builds of the step kernel, chosen per handle from the batch size (choose_variant):
+ *   latency    WPB = 4 warps per block, 254 registers (8 warps per SM): shortest per-warp dependent
+ *              chain; best while the batch is a single resident wave (<= 8k envs);
+ *   throughput WPB = 8, capped at 128 registers (16 warps per SM, 320 B of spills): +30 % once
+ *              several waves are resident.
+ * WPB > 1 with a block barrier per substep keeps the warps of an SM on the same instruction lines:
+ * the substep body is ~54 KB of straight-line SASS against a 32 KB L1.5 instruction cache, so every
+ * substep streams its code from L2, and warps that drift apart each pay for the fetch
+ * (profiles/r1_sweep_wpb.txt: +6 % at 4096 envs, +38 % at 64k envs against one warp per block).
+ * Eight envs per warp always: narrower warps were measured slower at every size
+ * (profiles/r1_sweep_epw.txt). */
+template <int NJL, int MINB, int WPB>
+__global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const __grid_constant__ StepArgs args) {
   __shared__ Smem sm;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;      /* warp in block */
   const SimConst& sc = args.sc;
   {
     const float* src = reinterpret_cast<const float*>(&args.mc.leg[0]);
     float* dst = reinterpret_cast<float*>(&sm.leg[0]);
-    for (int i = tid; i < (int)(sizeof(LegConst) * 4 / sizeof(float)); i += kBlockThreads) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(LegConst) * 4 / sizeof(float)); i += kBlockThreads * WPB) dst[i] = src[i];
   }
   __syncthreads();
   const int nsub = (args.mode == MODE_SUBSTEP) ? 1 : sc.frame_skip;
 
   const DevArrays& d = args.d;
-  const int el = (tid >> 2) % EPW, leg = tid & 3;
-  const int env = blockIdx.x * EPW + el;
-  const bool valid = ((tid >> 2) < EPW) && env < args.n;
+  const int el = tid >> 2, leg = tid & 3;
+  const int env = (blockIdx.x * WPB + wib) * 8 + el;
+  const bool valid = env < args.n;
   const int e = valid ? env : args.n - 1;
   const long long gid = args.env_id_offset + e;
   const int D0 = args.D0;
@@ -446,6 +452,7 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) step_kernel(const __grid_
 
   bk.nc_sum = 0; bk.sweep_feet = 0;
   for (int s = 0; s < nsub; s++) {                  /* frame_skip x p.stepSimulation() (solo.py:264-265) */
+    if (WPB > 1) __syncthreads();   /* keep the warps of a block on the same instruction lines */
     const bool torque_on = (s == 0) || sc.torque_hold; /* SURVEY F4 */
     float tau_s[NJL];
 #pragma unroll
@@ -840,8 +847,7 @@ struct SoloHandle {
   ModelConst mc;
   SimConst sc;
   int n, njl, nj, A, D0, D, device, K, cap;
-  int epw;   /* environments per warp of the step kernel (8, 4 or 2) */
-  int regs128;  /* SOLO_STEP_REGS=128: the 16-warps-per-SM build of the step kernel (large batches) */
+  int throughput;  /* which build of the step kernel this handle launches (choose_throughput) */
   uint64_t seed;
   long long env_id_offset;
   float goal_radius;
@@ -877,27 +883,26 @@ static StepArgs make_step_args(SoloHandle* h, int mode, int n, const float* in, 
   a.force_settle = -1;
   return a;
 }
-template <int EPW, int MINB>
-static void launch_step_epw(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
-  const int blocks = (a.n + EPW - 1) / EPW;
-  if (h->njl == 3) step_kernel<3, EPW, MINB><<<blocks, kBlockThreads, 0, s>>>(a);
-  else step_kernel<2, EPW, MINB><<<blocks, kBlockThreads, 0, s>>>(a);
+template <int MINB, int WPB>
+static void launch_step_variant(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
+  const int blocks = (a.n + 8 * WPB - 1) / (8 * WPB);
+  if (h->njl == 3) step_kernel<3, MINB, WPB><<<blocks, kBlockThreads * WPB, 0, s>>>(a);
+  else step_kernel<2, MINB, WPB><<<blocks, kBlockThreads * WPB, 0, s>>>(a);
 }
 static void launch_step(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
-  if (h->regs128) launch_step_epw<8, 16>(h, a, s);
-  else if (h->epw == 2) launch_step_epw<2, 1>(h, a, s);
-  else if (h->epw == 4) launch_step_epw<4, 1>(h, a, s);
-  else launch_step_epw<8, 1>(h, a, s);
+  if (h->throughput) launch_step_variant<2, 8>(h, a, s);
+  else launch_step_variant<1, 4>(h, a, s);
   h->launches++;
 }
-/* Environments per warp.  Measured on B200 (profiles/r1_sweep_epw.txt): full warps win at every
- * batch size, because a warp's step time is set by its own dependent chain and does not shrink when
- * lanes idle; the narrower variants stay selectable (SOLO_ENVS_PER_WARP) for experiments. */
-static int choose_epw(int n, int device) {
-  (void)n; (void)device;
-  const char* ev = getenv("SOLO_ENVS_PER_WARP");
-  if (ev) { int v = atoi(ev); if (v == 2 || v == 4 || v == 8) return v; }
-  return 8;
+/* latency build up to 8192 envs (one resident wave of 8 warps per SM), throughput build beyond;
+ * SOLO_STEP_VARIANT=latency|throughput overrides.  Results are bit-reproducible within a build
+ * (and therefore across shardings that stay within one); the two builds differ in the last bits
+ * because the compiler contracts and schedules the arithmetic differently. */
+static int choose_throughput(int n) {
+  const char* ev = getenv("SOLO_STEP_VARIANT");
+  if (ev && ev[0] == 'l') return 0;
+  if (ev && ev[0] == 't') return 1;
+  return n > 8192;
 }
 static ResetArgs make_reset_args(SoloHandle* h, int n, const uint8_t* mask, float* obs) {
   ResetArgs a;
@@ -980,8 +985,7 @@ int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_
   h->device = device; h->seed = seed; h->env_id_offset = env_id_offset;
   h->goal_radius = (float)params->goal_radius;
   h->was_reset = false; h->launches = 0;
-  h->epw = choose_epw(num_envs, device);
-  { const char* ev = getenv("SOLO_STEP_REGS"); h->regs128 = (ev && atoi(ev) == 128); if (h->regs128) h->epw = 8; }
+  h->throughput = choose_throughput(num_envs);
   h->K = params->settle_max - params->settle_min; if (h->K < 1) h->K = 1;
   h->cap = num_envs > h->K ? num_envs : h->K;
   h->s_act = h->s_obs = h->s_rew = h->s_done = nullptr;

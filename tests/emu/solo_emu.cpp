@@ -95,7 +95,7 @@ static void emu_substep(Emu* e, const float* tau) {
     PgsLane pl[4];
     for (int l = 0; l < 4; l++) {
       float rows[3][kRows];
-      for (int j = 0; j < 4; j++) assemble_block<NJL>(ln[l], j, ln[j].K, rows);
+      for (int j = 0; j < 4; j++) assemble_block<NJL>(ln[l], l, j, ln[j].K, rows);
       pgs_lane_init<NJL>(ln[l], l, rows, mask, pl[l]);
     }
     for (int it = 0; it < sc.iters; it++) {

@@ -165,11 +165,14 @@ def _hold_torque(s, nj, target, kp=3.0, kd=0.05):
     return np.clip(kp * (target - s[:, 13:13 + nj]) - kd * s[:, 13 + nj:], -3, 3)
 
 
+@pytest.mark.parametrize("build", ["latency", "throughput"])
 @pytest.mark.parametrize("robot", ROBOTS)
-def test_contact_substep_1e3(robot):
+def test_contact_substep_1e3(robot, build, monkeypatch):
     """Bent-leg stance under a joint PD hold + noise: 3-4 feet in contact.  Identical
     fp32-representable states injected before every substep (solo_set_state / solo_substep /
-    solo_get_state / solo_get_contacts)."""
+    solo_get_state / solo_get_contacts).  Both builds of the step kernel (254 registers, 4 warps per
+    block / 128 registers, 8 warps per block) are held to the same bound."""
+    monkeypatch.setenv("SOLO_STEP_VARIANT", build)
     rng = np.random.default_rng(24)
     n = 64
     sim, m, p = make_sim(robot, n)
@@ -231,7 +234,7 @@ def test_env_rollout_with_reset(robot, task, control, H):
             df[fl] = 0.0
             # free-running trajectories (up to 12 env steps of contact dynamics without re-injection):
             # glue logic, not numerics.  fp32-vs-fp64 differences grow ~10x per 4 env steps through the contact
-            # events of a flailing robot (tools/dbg_rollout.py: 1e-5 after one step, up to 3e-2 on the
+            # events of a flailing robot (1e-5 after one step, up to 3e-2 on the
             # angular velocity after 11), so the bound is 10 % of the slot's magnitude; the per-step numerics
             # are bounded by the 1e-5 / 1e-6 / 1e-3 tests above
             assert (df / np.maximum(1.0, np.abs(oo))).max() < 1e-1
@@ -251,6 +254,28 @@ def test_env_rollout_with_reset(robot, task, control, H):
     assert episodes >= nref * 2
     assert flag_bad <= 0.01 * flag_cmp, (flag_bad, flag_cmp)
     env.close()
+
+
+def test_builds_agree_on_a_rollout(monkeypatch):
+    """The latency and throughput builds run the same source: one env step from the same state agrees to
+    float noise (they are not bit-identical: the compiler contracts and schedules differently)."""
+    from solorl_b200.envs import SoloVecEnv
+    cfg = make_config("solo12", task="walk", H=1)
+    outs = []
+    for build in ("latency", "throughput"):
+        monkeypatch.setenv("SOLO_STEP_VARIANT", build)
+        env = SoloVecEnv(cfg, 256, device="cuda:0", seed=4)
+        env.reset()
+        g = torch.Generator(device="cuda").manual_seed(3)
+        a = torch.rand(256, 12, device="cuda", generator=g) * 2 - 1
+        o, r, d, _ = env.step(a)
+        outs.append((o.clone(), r.clone(), d.clone()))
+        env.close()
+    assert torch.equal(outs[0][2], outs[1][2])
+    assert (outs[0][1] - outs[1][1]).abs().max() < 1e-4
+    df = obs_diff(outs[0][0].cpu().numpy(), outs[1][0].cpu().numpy(), 38)
+    df[:, flag_slots(38, 12, 2)] = 0
+    assert df.max() < 1e-3
 
 
 def test_step_before_reset_is_an_error():

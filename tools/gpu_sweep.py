@@ -1,5 +1,5 @@
-"""Timing sweep of the step kernel over envs-per-warp and batch size (run on a GPU box).
-Usage: python tools/gpu_sweep.py [n1,n2,...] [epw1,epw2,...]"""
+"""Timing sweep of the step kernel over its two builds and the batch size (run on a GPU box).
+Usage: python tools/gpu_sweep.py [n1,n2,...] [latency,throughput,auto]"""
 import os
 import sys
 
@@ -9,11 +9,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from solorl_b200.envs import SoloVecEnv  # noqa: E402
 
 
-def time_cfg(name, n, epw, task="walk", K=200, extra=None):
-    if epw:
-        os.environ["SOLO_ENVS_PER_WARP"] = str(epw)
+def time_cfg(name, n, variant, task="walk", K=200, extra=None):
+    if variant and variant != "auto":
+        os.environ["SOLO_STEP_VARIANT"] = str(variant)
     else:
-        os.environ.pop("SOLO_ENVS_PER_WARP", None)
+        os.environ.pop("SOLO_STEP_VARIANT", None)
     cfg = {"model_urdf": name, "mode": "headless", "episode_length": 400, "frame_skip": 4,
            "control": "torque", "task": task, "num_history_stack": 1}
     cfg.update(extra or {})
@@ -41,13 +41,13 @@ def time_cfg(name, n, epw, task="walk", K=200, extra=None):
 
 def main():
     ns = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [4096, 16384, 65536]
-    epws = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8, 4, 2]
+    epws = sys.argv[2].split(",") if len(sys.argv) > 2 else ["latency", "throughput"]
     print(torch.cuda.get_device_name(0), flush=True)
     for name in ("solo12", "solo8"):
         for n in ns:
             for epw in epws:
                 ms, nc, sw, ssum = time_cfg(name, n, epw)
-                print(f"{name} n={n} epw={epw}: {ms * 1e3:8.1f} us/step  {n / ms * 1e3:.3e} env-steps/s  "
+                print(f"{name} n={n} build={epw}: {ms * 1e3:8.1f} us/step  {n / ms * 1e3:.3e} env-steps/s  "
                       f"contacts/substep {nc:.2f} sweeps {sw:.1f} state-checksum {ssum:.6f}", flush=True)
 
 
