@@ -12,7 +12,7 @@ import os
 from .abi import SoloEpisodeStats, SoloModelTable, SoloSimParams
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsolo_b200.so")
+LIB_PATH = os.environ.get("SOLO_B200_LIB", os.path.join(_PKG, "libsolo_b200.so"))   # override: A/B builds
 _lib = None
 
 # every symbol include/solo_b200.h declares (tests check the export list against the header)

@@ -102,18 +102,27 @@ SOLO_HD float solo_rsqrt(float x) {   /* x >= 1e-30: one MUFU.RSQ, no denormal f
   return 1.0f / sqrtf(x);
 #endif
 }
-/* Joint-angle sine/cosine.  Device: one Cody-Waite step by 2 pi (|x| <= 100 rad, the joint range is
- * +-10) then MUFU.SIN / MUFU.COS, whose absolute error on [-pi, pi] is 2^-21.4: 8 instructions against
- * the ~80 of sincosf with its slow-path code; the contact-free 1e-5 parity holds with margin (tests). */
+/* Joint-angle sine/cosine to ~1 ulp without sincosf's slow-path code: three-part Cody-Waite reduction
+ * by pi/2 (exact for |x| <= 100 rad; the joint range is +-10) and the Cephes single-precision minimax
+ * polynomials on [-pi/4, pi/4].  ~25 instructions.  (MUFU.SIN/COS would be 10, but their 4e-7 absolute
+ * error becomes a 1e-7 m foot-height error, which the contact rows amplify by 1/dt: measured, it doubled
+ * the median single-substep error against the oracle and produced rare 2e-3 outliers.)  The same code
+ * runs on the host, so the CPU replay of the lane program stays bit-comparable. */
 SOLO_HD void solo_sincos(float x, float* s, float* c) {
-#if defined(__CUDA_ARCH__)
-  const float k = rintf(x * 0.15915494309189535f);
-  float r = fmaf(k, -6.2831854820251465f, x);
-  r = fmaf(k, 1.7484555e-7f, r);
-  *s = __sinf(r); *c = __cosf(r);
-#else
-  *s = sinf(x); *c = cosf(x);
-#endif
+  const float kf = rintf(x * 0.63661977236758134f);
+  const int k = (int)kf;
+  float r = fmaf(kf, -1.5703125f, x);
+  r = fmaf(kf, -4.837512969970703125e-4f, r);
+  r = fmaf(kf, -7.54978995489188216e-8f, r);
+  const float z = r * r;
+  float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), z * r, r);
+  float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f), z * z,
+                  fmaf(-0.5f, z, 1.0f));
+  const bool swap = (k & 1) != 0;
+  float sv = swap ? cp : sp;
+  float cv = swap ? sp : cp;
+  *s = (k & 2) ? -sv : sv;
+  *c = ((k + 1) & 2) ? -cv : cv;
 }
 /* 1/x to within an ulp: MUFU.RCP and one Newton step, no denormal/slow-path code (x is a joint-axis
  * inertia, an LDL pivot or a Delassus diagonal: positive and far from the denormal range). */
@@ -680,15 +689,17 @@ SOLO_HD void pgs_normal_candidate(const PgsLane& pl, float& nv, float& d, float&
 SOLO_HD void pgs_cone_candidate(const PgsLane& pl, float mu, float& nA, float& nB, float& dA, float& dB,
                                 float& rv) {
   /* Bullet clamps sA to +-|lim sin(atan2(sA,sB))| and sB to +-|lim cos(.)|, i.e. it scales the pair
-   * (sA,sB) back onto the circle of radius lim when it lies outside: (sA,sB) * min(1, lim/|s|). */
+   * (sA,sB) back onto the circle of radius lim when it lies outside: (sA,sB) * min(1, lim/|s|).
+   * Written for the shortest dependent chain from g to the impulse change: the 1e-30 guard rides in
+   * the first FMA instead of a max, and d = s*scale - lambda is one FMA instead of multiply + subtract. */
   const float lim = mu * pl.lam[0];
   const float sA = pl.g[1], sB = pl.g[2];
-  const float n2 = fmaxf(sA * sA + sB * sB, 1e-30f);
+  const float n2 = fmaf(sB, sB, fmaf(sA, sA, 1e-30f));
   const float sc = fminf(lim * solo_rsqrt(n2), 1.0f);
   nA = sA * sc;
   nB = sB * sc;
-  dA = nA - pl.lam[1];
-  dB = nB - pl.lam[2];
+  dA = fmaf(sA, sc, -pl.lam[1]);
+  dB = fmaf(sB, sc, -pl.lam[2]);
   rv = dA * pl.diag[1] + dB * pl.diag[2];
 }
 /* candidate for one friction row (pyramid), q = 0/1 */
