@@ -241,6 +241,14 @@ int solo_get_feet(SoloHandle* h, float* d_out, void* stream);
 /* Episode records of the last step (see SoloEpisodeStats). d_stats: SoloEpisodeStats[N]. */
 int solo_episode_stats(SoloHandle* h, SoloEpisodeStats* d_stats, void* stream);
 
+/* Fold the episode records of the envs whose d_done flag is set (the flags solo_step just wrote) into
+ * running totals on the device — the trainer's episode logging (agents/ppo/train.py:90-100,
+ * agents/td3/train.py:108-115) without reading an info dict per env and step.
+ * d_acc double[13]: [0] episodes, [1] sum episode_reward, [2] sum episode_return, [3] sum length,
+ * [4] sum success, [5..9] sums of the five dr/ terms, [10] min return, [11] max return, [12] max length.
+ * The caller initialises d_acc (zeros; +inf / -inf / 0 for [10..12]). */
+int solo_accumulate_episode_stats(SoloHandle* h, const float* d_done, double* d_acc, void* stream);
+
 /* Curriculum hook (increment_goal_radius, solo.py:332-334). */
 int solo_set_goal_radius(SoloHandle* h, double goal_radius);
 

@@ -78,7 +78,9 @@ class PPO:
         self.entropy_coef = entropy_coef
         self.max_grad_norm = max_grad_norm
         self.use_clipped_value_loss = use_clipped_value_loss
-        self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, weight_decay=l2_coef)
+        p0 = next(actor_critic.parameters())
+        # fused Adam: one multi-tensor launch instead of ~10 per parameter tensor (same arithmetic)
+        self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, weight_decay=l2_coef, fused=bool(p0.is_cuda))
         self.grad_sync = FlatGradAllReduce(actor_critic.parameters())
 
     def update(self, storage):

@@ -30,50 +30,48 @@ _DR = ("dr/stand_rew", "dr/joint_pose_rew", "dr/torque_rew", "dr/roll_pitch_bala
 
 
 class EpisodeTracker:
-    """Device-side statistics of finished episodes (what train.py:90-100 appends to its deques)."""
+    """Device-side statistics of finished episodes (what train.py:90-100 appends to its deques): one
+    fused launch per step (``solo_accumulate_episode_stats``) into a 13-double accumulator that is read
+    once per log interval."""
 
     def __init__(self, device):
-        self.device = device
-        # count, sum last-step reward, sum return, sum length, sum success, 5 x dr sums
-        self.acc = torch.zeros(10, dtype=torch.float64, device=device)
-        self._ext0 = torch.tensor([float("inf"), float("-inf"), 0.0], dtype=torch.float32, device=device)
-        self.ext = self._ext0.clone()      # min return, max return, max length
+        self.device = torch.device(device)
+        self._init = torch.tensor([0.0] * 10 + [float("inf"), float("-inf"), 0.0], dtype=torch.float64, device=device)
+        self.acc = self._init.clone()
 
     def clear(self):
-        """In place: the tensors are baked into the captured rollout graph."""
-        self.acc.zero_()
-        self.ext.copy_(self._ext0)
+        """In place: the tensor is baked into the captured rollout graph."""
+        self.acc.copy_(self._init)
 
     def update(self, sim, done):
-        f, i = sim.episode_stats_device()
-        m = done > 0.5
-        md = m.to(torch.float64)
-        cols = torch.stack([torch.ones_like(md), f[:, 0].double(), f[:, 1].double(), i[:, 2].double(),
-                            i[:, 3].double(), f[:, 6].double(), f[:, 7].double(), f[:, 8].double(),
-                            f[:, 9].double(), f[:, 10].double()], dim=0)
-        self.acc.add_((cols * md).sum(dim=1))
-        ret = f[:, 1]
-        lo = torch.where(m, ret, torch.full_like(ret, float("inf"))).min()
-        hi = torch.where(m, ret, torch.full_like(ret, float("-inf"))).max()
-        ln = torch.where(m, i[:, 2].float(), torch.zeros_like(ret)).max()
-        self.ext.copy_(torch.stack([torch.minimum(self.ext[0], lo), torch.maximum(self.ext[1], hi),
-                                    torch.maximum(self.ext[2], ln)]))
+        if self.acc.is_cuda:
+            sim.accumulate_episode_stats(done, self.acc)
+        else:                                    # host-side logic tests: same arithmetic with torch ops
+            f, i = sim.episode_stats_device()
+            m = done > 0.5
+            if bool(m.any()):
+                cols = [torch.ones_like(f[:, 0]), f[:, 0], f[:, 1], i[:, 2].float(), i[:, 3].float(), f[:, 6],
+                        f[:, 7], f[:, 8], f[:, 9], f[:, 10]]
+                self.acc[:10] += torch.stack([c[m].double().sum() for c in cols])
+                self.acc[10] = torch.minimum(self.acc[10], f[m, 1].double().min())
+                self.acc[11] = torch.maximum(self.acc[11], f[m, 1].double().max())
+                self.acc[12] = torch.maximum(self.acc[12], i[m, 2].double().max())
 
     def fetch(self, clear=True):
         """One host sync; totals are summed over ranks when torch.distributed is up."""
-        acc, ext = self.acc.clone(), self.ext.clone()
+        acc = self.acc.clone()
         if dist_ready():
-            torch.distributed.all_reduce(acc)
-            mn, mx = ext[:1].clone(), ext[1:].clone()
+            sums, mn, mx = acc[:10].clone(), acc[10:11].clone(), acc[11:].clone()
+            torch.distributed.all_reduce(sums)
             torch.distributed.all_reduce(mn, op=torch.distributed.ReduceOp.MIN)
             torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
-            ext = torch.cat([mn, mx])
-        a, e = acc.tolist(), ext.tolist()
+            acc = torch.cat([sums, mn, mx])
+        a = acc.tolist()
         n = max(a[0], 1.0)
         out = {"episodes": int(a[0]), "episode_reward": a[1] / n, "episode_return": a[2] / n,
                "episode_length": a[3] / n, "success": a[4] / n,
-               "return_min": e[0], "return_max": e[1], "length_max": e[2]}
-        for k, v in zip(_DR, a[5:]):
+               "return_min": a[10], "return_max": a[11], "length_max": a[12]}
+        for k, v in zip(_DR, a[5:10]):
             out[k] = v / n
         if clear:
             self.clear()

@@ -809,6 +809,49 @@ __global__ void fill_cache_kernel(DevArrays d, int K, int H, int D0) {
     for (int i = 0; i < D0; i++) d.rc_hist[((size_t)t * H + h) * D0 + i] = d.hist[((size_t)h * d.cap + t) * D0 + i];
 }
 
+/* Trainer-side episode logging without a host round trip (agents/ppo/train.py:90-100 reads an info
+ * dict per finished env and step): fold the records of envs whose done flag is set into running
+ * totals.  acc[0..9] = count, sum episode_reward, sum episode_return, sum length, sum success, the
+ * five dr/ sums; acc[10..12] = min return, max return, max length.  Few envs finish per step, so
+ * plain atomics are enough. */
+__device__ __forceinline__ void atomic_min_double(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double((long long)assumed) <= v) break;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+  } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    if (__longlong_as_double((long long)assumed) >= v) break;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+  } while (assumed != old);
+}
+__global__ void episode_accumulate_kernel(const SoloEpisodeStats* __restrict__ stats, const float* __restrict__ done,
+                                          int n, double* acc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n || done[e] <= 0.5f) return;
+  const SoloEpisodeStats s = stats[e];
+  atomicAdd(acc + 0, 1.0);
+  atomicAdd(acc + 1, (double)s.episode_reward);
+  atomicAdd(acc + 2, (double)s.episode_return);
+  atomicAdd(acc + 3, (double)s.episode_length);
+  atomicAdd(acc + 4, (double)s.success);
+  atomicAdd(acc + 5, (double)s.dr_stand);
+  atomicAdd(acc + 6, (double)s.dr_joint_pose);
+  atomicAdd(acc + 7, (double)s.dr_torque);
+  atomicAdd(acc + 8, (double)s.dr_balance);
+  atomicAdd(acc + 9, (double)s.dr_progress);
+  atomic_min_double(acc + 10, (double)s.episode_return);
+  atomic_max_double(acc + 11, (double)s.episode_return);
+  atomic_max_double(acc + 12, (double)s.episode_length);
+}
+
 /* Reverse-scan GAE (agents/ppo/storage.py:35-55): one thread per env walks t = T-1..0;
  * consecutive threads read consecutive words of every [t] row, 20 B per (t, env). */
 __global__ void gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
@@ -1208,6 +1251,14 @@ int solo_episode_stats(SoloHandle* h, SoloEpisodeStats* d_stats, void* stream) {
   if (!h || !d_stats) return fail(h, SOLO_E_ARG, "null argument");
   CUDA_TRY(h, cudaMemcpyAsync(d_stats, h->d.stats, (size_t)h->n * sizeof(SoloEpisodeStats),
                               cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return SOLO_OK;
+}
+
+int solo_accumulate_episode_stats(SoloHandle* h, const float* d_done, double* d_acc, void* stream) {
+  if (!h || !d_done || !d_acc) return fail(h, SOLO_E_ARG, "null argument");
+  episode_accumulate_kernel<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d.stats, d_done, h->n, d_acc);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
   return SOLO_OK;
 }
 

@@ -98,6 +98,14 @@ class SoloSim:
         w = EPISODE_STATS_DTYPE.itemsize // 4
         return self._stats.view(torch.float32).view(self.n, w), self._stats.view(torch.int32).view(self.n, w)
 
+    def accumulate_episode_stats(self, done, acc):
+        """Fold the records of envs with done == 1 into ``acc`` (float64 [13] on the device, see
+        solo_accumulate_episode_stats); one small launch, no sync."""
+        if not (acc.is_cuda and acc.dtype == torch.float64 and acc.numel() == 13 and acc.is_contiguous()):
+            raise ValueError("acc must be a contiguous float64 CUDA tensor of 13 elements")
+        d = self._f32(done, (self.n,))
+        _lib.check(self.L.solo_accumulate_episode_stats(self.h, _ptr(d), _ptr(acc), self._stream()), self.h)
+
     def set_goal_radius(self, r):
         _lib.check(self.L.solo_set_goal_radius(self.h, float(r)), self.h)
 

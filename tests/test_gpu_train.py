@@ -106,3 +106,38 @@ def test_td3_train_runs_on_the_vec_env(tmp_path):
     assert torch.isfinite(out["replay"]._observations[:64 * 60]).all()
     nt = out["replay"]._not_terminal[:64 * 60]
     assert ((nt == 0) | (nt == 1)).all() and (nt == 0).any()
+
+
+def test_fused_episode_accumulator_matches_host_records():
+    """solo_accumulate_episode_stats against the same sums taken from the per-env records on the host."""
+    from solorl_b200.agents.train import EpisodeTracker
+    from solorl_b200.envs import SoloVecEnv
+    cfg = make_config("solo12", "pointgoal", "torque", 1, episode_length=8)
+    n = 512
+    env = SoloVecEnv(cfg, n, device="cuda:0", seed=5)
+    env.reset()
+    tr = EpisodeTracker(torch.device("cuda"))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    tot = dict(n=0, rew=0.0, ret=0.0, ln=0, succ=0, dr=np.zeros(5), mn=np.inf, mx=-np.inf, lmx=0)
+    for t in range(20):
+        a = torch.rand(n, 12, device="cuda", generator=g) * 3 - 1.5
+        obs, rew, done, infos = env.step(a)
+        tr.update(env.sim, done)
+        r = infos.done_records()
+        tot["n"] += len(r); tot["rew"] += float(r["episode_reward"].astype(np.float64).sum())
+        tot["ret"] += float(r["episode_return"].astype(np.float64).sum()); tot["ln"] += int(r["episode_length"].sum())
+        tot["succ"] += int(r["success"].sum())
+        for k, f in enumerate(("dr_stand", "dr_joint_pose", "dr_torque", "dr_balance", "dr_progress")):
+            tot["dr"][k] += float(r[f].astype(np.float64).sum())
+        if len(r):
+            tot["mn"] = min(tot["mn"], float(r["episode_return"].min())); tot["mx"] = max(tot["mx"], float(r["episode_return"].max()))
+            tot["lmx"] = max(tot["lmx"], int(r["episode_length"].max()))
+    st = tr.fetch()
+    assert st["episodes"] == tot["n"] > n
+    assert abs(st["episode_return"] - tot["ret"] / tot["n"]) < 1e-6 * max(1, abs(tot["ret"] / tot["n"]))
+    assert abs(st["episode_reward"] - tot["rew"] / tot["n"]) < 1e-6 and abs(st["episode_length"] - tot["ln"] / tot["n"]) < 1e-9
+    assert abs(st["success"] - tot["succ"] / tot["n"]) < 1e-9
+    assert abs(st["dr/stand_rew"] - tot["dr"][0] / tot["n"]) < 1e-6 and abs(st["dr/progress_rew"] - tot["dr"][4] / tot["n"]) < 1e-5
+    assert st["return_min"] == tot["mn"] and st["return_max"] == tot["mx"] and st["length_max"] == tot["lmx"]
+    assert tr.fetch()["episodes"] == 0
+    env.close()
