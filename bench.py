@@ -176,6 +176,40 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def time_policy_rollout(cfg, n, dev, rank, world, barrier, T=32, reps=10):
+    """env-steps/s of policy rollouts: Policy (agents/ppo/policy.py layout, init_layer orthogonal gain sqrt 2,
+    log-std 0), torch.manual_seed(1), stochastic sampling, rollout buffer appends included."""
+    import torch
+    from solorl_b200.agents.policy import Policy
+    from solorl_b200.agents.storage import OPBuffer
+    from solorl_b200.agents.train import EpisodeTracker, Rollout
+    from solorl_b200.envs import make_vec_envs
+    torch.manual_seed(1)
+    envs = make_vec_envs(cfg, n, device=dev, seed=2, env_id_offset=rank * n)
+    ac = Policy(envs.observation_space.shape, envs.action_space, None, {"hidden_size": 64}).to(dev)
+    buf = OPBuffer(T, n, envs.observation_space.shape, envs.action_space.shape[0], dev)
+    buf.obs[0].copy_(envs.reset())
+    ro = Rollout(envs, ac, buf, EpisodeTracker(dev), T, use_graph=True)
+    for _ in range(3):
+        ro(); buf.reset()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ro(); buf.reset()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    envs.close()
+    return {"value": world * n * T * reps / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms / (T * reps),
+            "rollout_steps": T, "cuda_graph": ro.graph is not None,
+            "what": "policy act + env step + rollout-buffer append per step, device resident"}
+
+
 def run_ours(args):
     import torch
     from solorl_b200 import _lib, build
@@ -272,6 +306,15 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = world * n * args.steps / e2e_s
 
+    # ---- policy rollout (reference-shaped MLP 64-64 tanh policy, stochastic actions), one CUDA graph of
+    #      T x (act -> env step -> buffer append); reported next to the random-action figure -------------
+    policy_rollout = None
+    if not args.no_policy_rollout:
+        try:
+            policy_rollout = time_policy_rollout(cfg, n, dev, rank, world, barrier)
+        except Exception as e:      # the headline metric does not depend on it
+            policy_rollout = {"error": repr(e)[:200]}
+
     if rank != 0:
         env.close()
         return
@@ -297,7 +340,11 @@ def run_ours(args):
     abytes = algorithmic_bytes_per_env_step(nj, D) * n
     roofline = {
         "bound": "fp32", "kernel": "step_kernel<3>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None,
+        "frac": achieved / peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this workload
+        # (profiles/r1g_step_kernel_ncu_full.txt); only valid for the default 4096-env Solo12 workload
+        "traffic": 1259008 if (n == ENVS_PER_GPU) else None,
+        "traffic_unit": "bytes per launch (algorithmic: %d)" % (algorithmic_bytes_per_env_step(nj, D) * n),
         "peak_source": "FP32 FMA microbenchmark measured live in this run (solo_bench_fma_peak)" if rc == 0
         else "fallback 148 SM x 128 lanes x 2 x 1.965 GHz",
         "algorithmic_flops_per_env_step": algorithmic_flops_per_env_step(nj, nc_sum, sweep_feet),
@@ -315,7 +362,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n, "robot": "solo12", "task": "walk", "control": "torque",
                    "num_history_stack": 1, "episode_length": 400, "solver_iters": 50,
-                   "solver_residual_threshold": 1e-7, "reset_mode": "cached",
+                   "solver_residual_threshold": 1e-7, "reset_mode": "cached", "step_kernel_build": "latency" if n <= 8192 else "throughput",
                    "l2": "flushed (256 MiB write) between timed steps; per-step CUDA events summed",
                    "parallelism": f"env-shard x{world}"},
         "clocks": clocks, "gpu_launches": int(launches),
@@ -324,6 +371,7 @@ def run_ours(args):
                 "api": "solo_step_host (pinned host buffers, one sync per step)"},
         "roofline": roofline,
         "back_to_back_ms_per_step": b2b_ms, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
+        "policy_rollout": policy_rollout,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
@@ -341,6 +389,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-policy-rollout", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
