@@ -150,6 +150,8 @@ typedef struct SoloEpisodeStats {
   int32_t timeout;       /* info['timeout'] */
   int32_t goals_reached;
   float dr_stand, dr_joint_pose, dr_torque, dr_balance, dr_progress; /* the 'dr/...' sums */
+  int32_t nan;           /* 1: the episode was ended by the non-finite-state guard (the reference only
+                          * guards its gait envs, baseControlEnv.py:171-175,389-397: zero obs, done, hard reset) */
 } SoloEpisodeStats;
 
 typedef struct SoloHandle SoloHandle;

@@ -99,6 +99,7 @@ class SoloEpisodeStats(C.Structure):
         ("dr_torque", C.c_float),
         ("dr_balance", C.c_float),
         ("dr_progress", C.c_float),
+        ("nan", C.c_int32),
     ]
 
 
@@ -106,7 +107,8 @@ EPISODE_STATS_DTYPE = np.dtype([
     ("episode_reward", np.float32), ("episode_return", np.float32),
     ("episode_length", np.int32), ("success", np.int32), ("timeout", np.int32),
     ("goals_reached", np.int32), ("dr_stand", np.float32), ("dr_joint_pose", np.float32),
-    ("dr_torque", np.float32), ("dr_balance", np.float32), ("dr_progress", np.float32)])
+    ("dr_torque", np.float32), ("dr_balance", np.float32), ("dr_progress", np.float32),
+    ("nan", np.int32)])
 assert EPISODE_STATS_DTYPE.itemsize == C.sizeof(SoloEpisodeStats)
 
 

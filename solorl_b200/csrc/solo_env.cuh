@@ -66,8 +66,16 @@ struct StepOutcome {
  * sum_q  = sum over joints of |q| (stand) or q^2 (walk, pointgoal);  sum_a2 = sum a^2 over the raw action.
  * progress = robot.progress (pointgoal).  Updates book (timestep must already be incremented). */
 SOLO_HD StepOutcome step_outcome(const SimConst& sc, const BaseState& st, int nj, float sum_q,
-                                 float sum_a2, float progress_pg, EnvBook& bk) {
+                                 float sum_a2, float progress_pg, EnvBook& bk, bool bad_state = false) {
   StepOutcome o;
+  if (bad_state) {
+    /* non-finite state (NaN/Inf actions or a blown-up solve): end the episode as a failure and let the
+     * auto-reset replace the state; nothing non-finite enters the episode sums */
+    o.reward = -10.f; o.done = 1; o.success = 0; o.timeout = 0;
+    bk.reward_sum = isfinite(bk.reward_sum) ? bk.reward_sum + o.reward : o.reward;
+    for (int i = 0; i < 5; i++) bk.dr[i] = isfinite(bk.dr[i]) ? bk.dr[i] : 0.f;
+    return o;
+  }
   float z = st.p[2];
   float stand = (z > sc.stand_z ? 1.0f : 0.0f) * 0.5f;            /* :96 */
   float jp = -0.1f * (sum_q / (float)nj);                         /* :101,:113,:131 */

@@ -484,8 +484,14 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
       sq += (sc.task == 0) ? fabsf(ln.q[k]) : ln.q[k] * ln.q[k];
       sa += act[k] * act[k];
     }
-    sq = sum4(sq); sa = sum4(sa);
-    StepOutcome o = step_outcome(sc, st, 4 * NJL, sq, sa, progress, bk);
+    /* non-finite-state guard: 0 * x is NaN exactly when x is NaN or Inf */
+    float chk = st.p[0] + st.p[1] + st.p[2] + st.q[0] + st.q[1] + st.q[2] + st.q[3] + st.v[0] + st.v[1] + st.v[2] +
+                st.w[0] + st.w[1] + st.w[2] + sa;
+#pragma unroll
+    for (int k = 0; k < NJL; k++) chk += ln.q[k] + ln.qd[k];
+    sq = sum4(sq); sa = sum4(sa); chk = sum4(chk * 0.f);
+    const bool bad_state = !(chk == 0.f);
+    StepOutcome o = step_outcome(sc, st, 4 * NJL, sq, sa, progress, bk, bad_state);
     if (valid && leg == 0) {
       args.reward[e] = o.reward;
       args.done[e] = o.done ? 1.0f : 0.0f;
@@ -498,6 +504,7 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
         s.goals_reached = bk.goals_env;
         s.dr_stand = bk.dr[0]; s.dr_joint_pose = bk.dr[1]; s.dr_torque = bk.dr[2];
         s.dr_balance = bk.dr[3]; s.dr_progress = bk.dr[4];
+        s.nan = bad_state ? 1 : 0;
         d.stats[e] = s;
       }
       /* worker auto-reset (agents/ppo/envs.py:38-40) */

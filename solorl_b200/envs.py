@@ -72,6 +72,7 @@ class LazyInfos:
         d["episode_reward"] = float(r["episode_reward"])    # last-step reward
         d["episode_return"] = float(r["episode_return"])    # sum of rewards (extension)
         d["goals_reached"] = int(r["goals_reached"])
+        d["nan"] = bool(r["nan"])                           # ended by the non-finite-state guard
         # keys the PPO loop reads but only BaseControlEnv provides
         d["max_velocity"] = 0.0
         d["min_force"] = 0.0

@@ -91,9 +91,9 @@ class SoloSim:
         return self._stats.cpu().numpy().view(EPISODE_STATS_DTYPE)
 
     def episode_stats_device(self):
-        """The same records without leaving the device: (float32 view [N,11], int32 view [N,11]) of
+        """The same records without leaving the device: (float32 view [N,12], int32 view [N,12]) of
         ``SoloEpisodeStats[N]``; columns 0,1,6..10 are floats (episode_reward, episode_return, dr/*),
-        columns 2..5 ints (episode_length, success, timeout, goals_reached).  No sync."""
+        columns 2..5 and 11 ints (episode_length, success, timeout, goals_reached, nan).  No sync."""
         _lib.check(self.L.solo_episode_stats(self.h, _ptr(self._stats), self._stream()), self.h)
         w = EPISODE_STATS_DTYPE.itemsize // 4
         return self._stats.view(torch.float32).view(self.n, w), self._stats.view(torch.int32).view(self.n, w)

@@ -321,6 +321,7 @@ int emu_step(void* h, const float* action, int auto_reset, float* obs, float* re
     stats->goals_reached = e->bk.goals_env;
     stats->dr_stand = e->bk.dr[0]; stats->dr_joint_pose = e->bk.dr[1]; stats->dr_torque = e->bk.dr[2];
     stats->dr_balance = e->bk.dr[3]; stats->dr_progress = e->bk.dr[4];
+    stats->nan = 0;
   }
   *reward = o.reward; *done = o.done;
   if (o.done) { e->need_reset = 1; if (auto_reset) emu_reset(h, obs); }

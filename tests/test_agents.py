@@ -140,7 +140,7 @@ class _FakeSim:
 
 def test_episode_tracker_accumulates_done_envs_only():
     n = 5
-    f = torch.zeros(n, 11); i = torch.zeros(n, 11, dtype=torch.int32)
+    f = torch.zeros(n, 12); i = torch.zeros(n, 12, dtype=torch.int32)
     f[:, 0] = torch.tensor([1., 2., 3., 4., 5.]); f[:, 1] = torch.tensor([10., 20., 30., 40., 50.])
     i[:, 2] = torch.tensor([5, 6, 7, 8, 9]); i[:, 3] = torch.tensor([1, 0, 1, 0, 1])
     f[:, 6] = 0.5

@@ -434,3 +434,56 @@ def test_single_env_facade():
         o, r, d, info = env.step(np.zeros(8))
     assert d and info["timeout"] and info["episode_length"] == 3
     env.close()
+
+
+@pytest.mark.parametrize("n", [1, 7, 37])
+def test_ragged_batch_sizes_match_the_full_batch_bitwise(n):
+    """Batches that do not fill a warp / a 4-warp block: env i of an n-env handle is env i of a 64-env one
+    (idle lanes mirror a valid env and never store)."""
+    from solorl_b200.envs import SoloVecEnv
+    cfg = make_config("solo12", task="pointgoal", H=2, episode_length=6)
+    small = SoloVecEnv(cfg, n, device="cuda:0", seed=11)
+    big = SoloVecEnv(cfg, 64, device="cuda:0", seed=11)
+    assert torch.equal(small.reset(), big.reset()[:n])
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for t in range(15):
+        a = torch.rand(64, 12, device="cuda", generator=g) * 2.4 - 1.2
+        o1, r1, d1, i1 = small.step(a[:n].contiguous())
+        o2, r2, d2, i2 = big.step(a)
+        assert torch.equal(o1, o2[:n]) and torch.equal(r1, r2[:n]) and torch.equal(d1, d2[:n])
+    assert torch.equal(small.sim.get_state(), big.sim.get_state()[:n])
+    small.close(); big.close()
+
+
+def test_non_finite_actions_end_the_episode_and_do_not_spread():
+    """NaN / Inf actions: the env ends as a failure (-10, done, info['nan']), auto-resets to a finite state,
+    and neighbouring envs of the same warp are untouched (bitwise equal to a run without the bad action)."""
+    from solorl_b200.envs import SoloVecEnv
+    cfg = make_config("solo12", task="walk", H=1, episode_length=50)
+    n = 32
+    a_env = SoloVecEnv(cfg, n, device="cuda:0", seed=13)
+    b_env = SoloVecEnv(cfg, n, device="cuda:0", seed=13)
+    a_env.reset(); b_env.reset()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    bad = [3, 17]
+    for t in range(6):
+        a = torch.rand(n, 12, device="cuda", generator=g) * 2 - 1
+        ab = a.clone()
+        if t == 2:
+            ab[3, 5] = float("nan"); ab[17, 0] = float("inf")
+        o1, r1, d1, i1 = a_env.step(a)
+        o2, r2, d2, i2 = b_env.step(ab)
+        assert torch.isfinite(o2).all() and torch.isfinite(r2).all()
+        good = [k for k in range(n) if k not in bad]
+        if t <= 2:
+            assert torch.equal(o1[good], o2[good]) and torch.equal(r1[good], r2[good])
+        if t == 2:
+            for k in bad:
+                assert d2[k] == 1 and r2[k] == -10.0
+                info = i2[k]
+                assert info["nan"] and not info["success"] and not info["timeout"] and info["episode_length"] == 3
+                assert np.isfinite(info["episode_return"])
+        if t > 2:
+            assert torch.equal(o1[good], o2[good])
+    assert torch.isfinite(b_env.sim.get_state()).all()
+    a_env.close(); b_env.close()
