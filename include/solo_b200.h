@@ -184,8 +184,10 @@ int solo_step(SoloHandle* h, const float* d_actions, float* d_obs, float* d_rewa
               float* d_done, void* stream);
 
 /* Same call with HOST buffers (the reference boundary is host numpy arrays,
- * agents/ppo/envs.py:189-196): H2D actions, step, D2H obs/reward/done, then one
- * stream synchronise.  Pinned buffers avoid a staging copy. */
+ * agents/ppo/envs.py:189-196): H2D actions, step, obs/reward/done back on the host, then one
+ * stream synchronise.  When the three output buffers are pinned (page-locked) the step kernel writes
+ * them itself through their device-mapped alias, as whole 128-byte lines while the launch is still
+ * running; pageable buffers go through device staging and three D2H copies. */
 int solo_step_host(SoloHandle* h, const float* h_actions, float* h_obs, float* h_reward,
                    float* h_done, void* stream);
 

@@ -84,6 +84,11 @@ struct ResetArgs {
   int reset_simulate, force_settle;
 };
 
+/* Observation rows of the eight envs of a warp are assembled in shared memory and leave the SM as
+ * whole 128-byte lines (8 x D contiguous floats per warp): the row pieces come from four lanes in
+ * 4-byte scraps, which is tolerable for HBM but not for the host-mapped output buffers of
+ * solo_step_host, where every store is a PCIe write. */
+constexpr int kStageD = 128;   /* rows up to 128 floats are staged (D = 76 / 84 for H = 1); longer ones go direct */
 struct Smem {
   LegConst leg[4];
 };
@@ -174,6 +179,17 @@ __device__ __forceinline__ void push_history(const DevArrays& d, const SimConst&
 }
 
 /* calc_state (solo.py:186-196): [cur, cur - hist[0], cur - hist[1], ...] */
+template <int NJL>
+__device__ __forceinline__ void write_obs_row(const DevArrays& d, const SimConst& sc, int D0, int e, int leg,
+                                              const RowPieces<NJL>& cur, float* row) {
+  store_pieces<NJL>(row, leg, sc.task, cur);
+  for (int h = 0; h < sc.H; h++) {
+    RowPieces<NJL> old, df;
+    load_pieces<NJL>(hist_row(d, D0, h, e), leg, sc.task, old);
+    diff_pieces<NJL>(cur, old, df);
+    store_pieces<NJL>(row + (size_t)(1 + h) * D0, leg, sc.task, df);
+  }
+}
 template <int NJL>
 __device__ __forceinline__ void write_obs(const DevArrays& d, const SimConst& sc, int D0, int D, int e, int leg,
                                           const RowPieces<NJL>& cur, float* obs) {
@@ -395,6 +411,7 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
 template <int NJL, int MINB, int WPB>
 __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const __grid_constant__ StepArgs args) {
   __shared__ Smem sm;
+  __shared__ __align__(16) float stage[WPB][8][kStageD];
   const int tid = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;      /* warp in block */
   const SimConst& sc = args.sc;
@@ -477,7 +494,9 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
     bk.timestep += 1;                               /* baseEnv.py:47 */
     RowPieces<NJL> cur;
     make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
-    if (valid) write_obs<NJL>(d, sc, D0, args.D, e, leg, cur, args.obs);
+    const bool staged = args.D <= kStageD;           /* uniform */
+    float* const row = staged ? &stage[wib][el][0] : args.obs + (size_t)e * args.D;
+    if (valid) write_obs_row<NJL>(d, sc, D0, e, leg, cur, row);
     float sq = 0.f, sa = 0.f;
 #pragma unroll
     for (int k = 0; k < NJL; k++) {
@@ -513,8 +532,24 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
                          args.reset_simulate, -1, st, ln, cforce, goal, potential, bk);
         if (!args.reset_simulate) {
           make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
-          write_obs<NJL>(d, sc, D0, args.D, e, leg, cur, args.obs);
+          write_obs_row<NJL>(d, sc, D0, e, leg, cur, row);
         }
+      }
+    }
+    if (staged) {                                     /* the warp's 8 x D floats leave as whole lines */
+      __syncwarp();
+      const int e0 = (blockIdx.x * WPB + wib) * 8;
+      const int nv = min(8, args.n - e0);
+      if ((args.D & 3) == 0) {
+        const int d4 = args.D >> 2;
+        for (int r = 0; r < nv; r++) {
+          float4* dst = reinterpret_cast<float4*>(args.obs + (size_t)(e0 + r) * args.D);
+          const float4* src = reinterpret_cast<const float4*>(&stage[wib][r][0]);
+          for (int j = tid; j < d4; j += 32) dst[j] = src[j];
+        }
+      } else {
+        for (int r = 0; r < nv; r++)
+          for (int j = tid; j < args.D; j += 32) args.obs[(size_t)(e0 + r) * args.D + j] = stage[wib][r][j];
       }
     }
   } else if (args.mode == MODE_SETTLE && active) {
@@ -1118,6 +1153,14 @@ int solo_step(SoloHandle* h, const float* d_actions, float* d_obs, float* d_rewa
   return SOLO_OK;
 }
 
+/* device-visible alias of a pinned (page-locked, UVA-mapped) host buffer, or NULL */
+static float* mapped_alias(float* host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+  return static_cast<float*>(at.devicePointer);
+}
+
 int solo_step_host(SoloHandle* h, const float* h_actions, float* h_obs, float* h_reward, float* h_done, void* stream) {
   if (!h || !h_actions || !h_obs || !h_reward || !h_done) return fail(h, SOLO_E_ARG, "null argument to solo_step_host");
   if (!h->was_reset) return fail(h, SOLO_E_STATE, "env.reset() must be called before step");
@@ -1130,11 +1173,26 @@ int solo_step_host(SoloHandle* h, const float* h_actions, float* h_obs, float* h
     CUDA_TRY(h, cudaMalloc(&h->s_done, n * sizeof(float)));
   }
   CUDA_TRY(h, cudaMemcpyAsync(h->s_act, h_actions, n * h->A * sizeof(float), cudaMemcpyHostToDevice, s));
-  int rc = solo_step(h, h->s_act, h->s_obs, h->s_rew, h->s_done, stream);
-  if (rc != SOLO_OK) return rc;
-  CUDA_TRY(h, cudaMemcpyAsync(h_obs, h->s_obs, n * h->D * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(h, cudaMemcpyAsync(h_reward, h->s_rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(h, cudaMemcpyAsync(h_done, h->s_done, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  /* Pinned output buffers are written by the step kernel itself (whole 128-byte lines over PCIe as the
+   * warps finish, overlapping the rest of the launch) instead of by three copies after it; pageable
+   * buffers, and the simulate-mode reset whose settle launches rewrite observation rows, take the staged
+   * path.  SOLO_HOST_ZERO_COPY=0 forces the staged path. */
+  float* z_obs = mapped_alias(h_obs);
+  float* z_rew = mapped_alias(h_reward);
+  float* z_done = mapped_alias(h_done);
+  const char* ev = getenv("SOLO_HOST_ZERO_COPY");
+  const bool zero_copy = z_obs && z_rew && z_done && h->D <= kStageD && h->params.reset_mode == SOLO_RESET_CACHED &&
+                         !(ev && ev[0] == '0');
+  if (zero_copy) {
+    int rc = solo_step(h, h->s_act, z_obs, z_rew, z_done, stream);
+    if (rc != SOLO_OK) return rc;
+  } else {
+    int rc = solo_step(h, h->s_act, h->s_obs, h->s_rew, h->s_done, stream);
+    if (rc != SOLO_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h_obs, h->s_obs, n * h->D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h_reward, h->s_rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h_done, h->s_done, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
   CUDA_TRY(h, cudaStreamSynchronize(s));
   return SOLO_OK;
 }

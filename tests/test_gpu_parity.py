@@ -536,3 +536,28 @@ def test_full_size_contact_config_4096_envs():
         assert torch.isfinite(obs).all() and obs.shape == (4096, 64)
     assert done.sum().item() == 0 and (obs[:, 0] > 0.15).all() and (total / 4 > 0.5).all()
     env.close()
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_buffer_step_matches_device_step(pinned):
+    """solo_step_host (H2D actions, kernel, outputs on the host) against solo_step on a twin handle:
+    bit-identical observations / rewards / done flags, with pinned buffers (zero-copy outputs written by
+    the kernel) and with pageable ones (staged D2H copies)."""
+    from solorl_b200.envs import SoloVecEnv
+    cfg = make_config("solo12", task="walk", H=1, episode_length=7)
+    n = 203                                     # ragged: the last warp is partly idle
+    dev = SoloVecEnv(cfg, n, device="cuda:0", seed=6)
+    hst = SoloVecEnv(cfg, n, device="cuda:0", seed=6)
+    dev.reset(); hst.reset()
+    def mk(*shape):
+        t = torch.empty(*shape, dtype=torch.float32)
+        return t.pin_memory() if pinned else t
+    h_obs, h_rew, h_done = mk(n, 76), mk(n), mk(n)
+    h_obs.fill_(-7.0)
+    g = torch.Generator().manual_seed(12)
+    for t in range(12):
+        a = torch.rand(n, 12, generator=g) * 2 - 1
+        o, r, d, _ = dev.step(a.cuda())
+        hst.sim.step_host(a.numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
+        assert torch.equal(o.cpu(), h_obs) and torch.equal(r.cpu(), h_rew) and torch.equal(d.cpu(), h_done)
+    dev.close(); hst.close()
