@@ -292,12 +292,14 @@ def run_ours(args):
     h_obs = torch.empty(n, D, dtype=torch.float32).pin_memory()
     h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
     h_done = torch.empty(n, dtype=torch.float32).pin_memory()
+    np_act = [t.numpy() for t in h_act]
+    np_obs, np_rew, np_done = h_obs.numpy(), h_rew.numpy(), h_done.numpy()
     for i in range(3):
-        sim.step_host(h_act[i % 4].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
+        sim.step_host(np_act[i % 4], np_obs, np_rew, np_done)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        sim.step_host(h_act[i % 4].numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
+        sim.step_host(np_act[i % 4], np_obs, np_rew, np_done)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -368,7 +370,7 @@ def run_ours(args):
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * A * 4,
                 "d2h_bytes_per_step": n * (D + 2) * 4, "ms_per_step": e2e_s / args.steps * 1e3,
-                "api": "solo_step_host (pinned host buffers, one sync per step)"},
+                "api": "solo_step_host (pinned host buffers read and written by the step kernel through their mapped alias, one sync per step)"},
         "roofline": roofline,
         "back_to_back_ms_per_step": b2b_ms, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "policy_rollout": policy_rollout,

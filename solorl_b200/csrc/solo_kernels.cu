@@ -448,7 +448,19 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
 #pragma unroll
   for (int k = 0; k < NJL; k++) { tau[k] = 0.f; act[k] = 0.f; }
   if (args.mode == MODE_STEP) {                     /* apply_action (solo.py:224-259) */
+    /* the warp's 8 x A action words arrive as whole lines through the (still unused) observation stage:
+     * the actions may live in host-mapped memory (solo_step_host), where scattered 4-byte reads would each
+     * be a PCIe round trip */
+    const int e0w = (blockIdx.x * WPB + wib) * 8;
+    const bool tile_ok = (e0w + 8 <= args.n);       /* warp-uniform; ragged / idle warps read directly */
     const float* a = args.in + (size_t)e * args.A;
+    if (tile_ok) {
+      float* tile = &stage[wib][0][0];
+      const float* src = args.in + (size_t)e0w * args.A;
+      for (int j = tid; j < 8 * args.A; j += 32) tile[j] = src[j];
+      __syncwarp();
+      a = tile + el * args.A;
+    }
     float kp = sc.kp, kd = sc.kd;
     if (sc.control == 2) { kp = a[4 * NJL]; kd = a[4 * NJL + 1]; }
 #pragma unroll
@@ -456,6 +468,7 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
       act[k] = a[leg * NJL + k];
       tau[k] = action_to_torque(sc, act[k], ln.q[k], ln.qd[k], kp, kd);
     }
+    __syncwarp();                                   /* the stage is reused for the observation rows */
   } else if (args.mode == MODE_SUBSTEP) {
 #pragma unroll
     for (int k = 0; k < NJL; k++) tau[k] = args.in[(size_t)e * 4 * NJL + leg * NJL + k];
@@ -942,6 +955,7 @@ struct SoloHandle {
   std::string err;
   /* staging for solo_step_host */
   float *s_act, *s_obs, *s_rew, *s_done;
+  int host_zero_copy;   /* SOLO_HOST_ZERO_COPY != 0 */
 };
 
 static thread_local std::string g_err;
@@ -1074,6 +1088,7 @@ int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_
   h->K = params->settle_max - params->settle_min; if (h->K < 1) h->K = 1;
   h->cap = num_envs > h->K ? num_envs : h->K;
   h->s_act = h->s_obs = h->s_rew = h->s_done = nullptr;
+  { const char* ev = getenv("SOLO_HOST_ZERO_COPY"); h->host_zero_copy = !(ev && ev[0] == '0'); }
   memset(&h->d, 0, sizeof(h->d));
   h->d.cap = h->cap;
   const int H = params->num_history_stack;
@@ -1172,19 +1187,20 @@ int solo_step_host(SoloHandle* h, const float* h_actions, float* h_obs, float* h
     CUDA_TRY(h, cudaMalloc(&h->s_rew, n * sizeof(float)));
     CUDA_TRY(h, cudaMalloc(&h->s_done, n * sizeof(float)));
   }
-  CUDA_TRY(h, cudaMemcpyAsync(h->s_act, h_actions, n * h->A * sizeof(float), cudaMemcpyHostToDevice, s));
   /* Pinned output buffers are written by the step kernel itself (whole 128-byte lines over PCIe as the
    * warps finish, overlapping the rest of the launch) instead of by three copies after it; pageable
    * buffers, and the simulate-mode reset whose settle launches rewrite observation rows, take the staged
    * path.  SOLO_HOST_ZERO_COPY=0 forces the staged path. */
-  float* z_obs = mapped_alias(h_obs);
-  float* z_rew = mapped_alias(h_reward);
-  float* z_done = mapped_alias(h_done);
-  const char* ev = getenv("SOLO_HOST_ZERO_COPY");
-  const bool zero_copy = z_obs && z_rew && z_done && h->D <= kStageD && h->params.reset_mode == SOLO_RESET_CACHED &&
-                         !(ev && ev[0] == '0');
+  /* queried on every call (measured: no visible cost): a cached answer would go stale if the caller
+   * freed a pinned buffer and a pageable one landed on the same address */
+  float *z_obs = mapped_alias(h_obs), *z_rew = mapped_alias(h_reward), *z_done = mapped_alias(h_done);
+  const bool zero_copy = h->host_zero_copy && z_obs && z_rew && z_done && h->D <= kStageD &&
+                         h->params.reset_mode == SOLO_RESET_CACHED;
+  /* likewise a pinned action buffer is read by the kernel directly (three 128-byte lines per warp) */
+  const float* z_act = zero_copy ? mapped_alias(const_cast<float*>(h_actions)) : nullptr;
+  if (!z_act) CUDA_TRY(h, cudaMemcpyAsync(h->s_act, h_actions, n * h->A * sizeof(float), cudaMemcpyHostToDevice, s));
   if (zero_copy) {
-    int rc = solo_step(h, h->s_act, z_obs, z_rew, z_done, stream);
+    int rc = solo_step(h, z_act ? z_act : h->s_act, z_obs, z_rew, z_done, stream);
     if (rc != SOLO_OK) return rc;
   } else {
     int rc = solo_step(h, h->s_act, h->s_obs, h->s_rew, h->s_done, stream);
