@@ -561,3 +561,93 @@ def test_host_buffer_step_matches_device_step(pinned):
         hst.sim.step_host(a.numpy(), h_obs.numpy(), h_rew.numpy(), h_done.numpy())
         assert torch.equal(o.cpu(), h_obs) and torch.equal(r.cpu(), h_rew) and torch.equal(d.cpu(), h_done)
     dev.close(); hst.close()
+
+
+# ---- option variants of the step (every SoloSimParams switch the configs can reach) -----------------------
+def _one_step_vs_oracle(cfg, robot, n=32, steps=2, seed=31, nref=8, tol=5e-3):
+    """Reset + `steps` env steps on the GPU and in the oracle from the same seeds; returns the worst
+    observation / reward difference over the first `nref` envs (flags counted, Euler slots modulo the wrap)."""
+    from solorl_b200.envs import SoloVecEnv
+    env = SoloVecEnv(cfg, n, device="cuda:0", seed=seed)
+    ors = [OracleEnv(env.model, env.params, seed=seed, env_id=i) for i in range(nref)]
+    obs = env.reset().cpu().numpy()
+    blocks = 1 + int(cfg.get("num_history_stack", 0))
+    fl = flag_slots(ors[0].d0, env.sim.nj, blocks)
+    worst = 0.0
+    for i, o in enumerate(ors):
+        df = obs_diff(o.reset(), obs[i], o.d0); df[fl] = 0
+        worst = max(worst, df.max())
+    rng = np.random.default_rng(seed)
+    for t in range(steps):
+        a = rng.uniform(-1, 1, size=(n, env.sim.act_dim)).astype(np.float32)
+        ob, rw, dn, _ = env.step(torch.from_numpy(a).cuda())
+        ob, rw, dn = ob.cpu().numpy(), rw.cpu().numpy(), dn.cpu().numpy()
+        for i, o in enumerate(ors):
+            oo, r, d, info = o.step(a[i].astype(np.float64), auto_reset=True)
+            assert d == (dn[i] > 0.5)
+            df = obs_diff(oo, ob[i], o.d0); df[fl] = 0
+            worst = max(worst, (df / np.maximum(1.0, np.abs(oo))).max(), abs(r - rw[i]) / max(1.0, abs(r)))
+    env.close()
+    assert worst < tol, worst
+    return worst
+
+
+@pytest.mark.parametrize("extra", [dict(cone_friction=0), dict(torque_hold=1), dict(frame_skip=1), dict(frame_skip=8),
+                                   dict(num_history_stack=8), dict(solver_iters=5), dict(solver_residual_threshold=0.0),
+                                   dict(contact_erp=0.08), dict(friction=0.5)])
+def test_option_variants_against_oracle(extra):
+    """Pyramid friction, torque held over all substeps, other frame skips, the longest history the kernel
+    accepts, truncated / fixed-count solves, other ERP / friction: each against the oracle built from the
+    same params (one reset + two env steps, i.e. 5..11 settle steps and 2 x frame_skip contact substeps)."""
+    cfg = make_config("solo12", task="walk", control="torque", H=1, episode_length=50)
+    cfg.update(extra)
+    _one_step_vs_oracle(cfg, "solo12")
+
+
+def test_vpd_control_rollout_against_oracle():
+    cfg = make_config("solo8", task="stand", control="vpd", H=1, episode_length=50)
+    _one_step_vs_oracle(cfg, "solo8")
+
+
+def test_masked_reset_touches_only_the_masked_envs():
+    from solorl_b200.envs import SoloVecEnv
+    cfg = make_config("solo12", task="pointgoal", H=1, episode_length=50)
+    n = 40
+    env = SoloVecEnv(cfg, n, device="cuda:0", seed=17)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(4):
+        env.step(torch.rand(n, 12, device="cuda", generator=g) * 2 - 1)
+    before = env.sim.get_state().clone()
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    mask[[1, 8, 9, 33]] = 1
+    obs = env.sim.reset(mask).clone()
+    after = env.sim.get_state()
+    keep = mask == 0
+    assert torch.equal(before[keep], after[keep])
+    assert not torch.equal(before[~keep], after[~keep])
+    # a freshly reset env stands at the settled reset pose: z a little under 0.35, no joint velocity to speak of
+    assert ((after[~keep, 2] > 0.25) & (after[~keep, 2] < 0.36)).all()
+    # reset observations were written for the masked envs only
+    full = env.get_observation()
+    assert torch.equal(obs[~keep], full[~keep])
+    env.close()
+
+
+def test_episode_length_one_and_curriculum_hook():
+    from solorl_b200.envs import make_vec_envs
+    cfg = make_config("solo12", task="pointgoal", H=0, episode_length=1)
+    envs = make_vec_envs(cfg, 16, seed=2)
+    envs.reset()
+    obs, rew, done, infos = envs.step(torch.zeros(16, 12, device="cuda"))
+    assert done.sum().item() == 16 and all(infos[i]["timeout"] and not infos[i]["success"] for i in range(16))
+    assert all(infos[i]["episode_length"] == 1 for i in range(16))
+    r0 = envs.envs.venv.goal_radius
+    envs.increment_curriculum()                                      # solo.py:332-334
+    assert envs.envs.venv.goal_radius == r0 + 1.0
+    for _ in range(3):
+        obs, rew, done, infos = envs.step(torch.zeros(16, 12, device="cuda"))
+    goals = obs[:, -2:] * 2.0                                         # [x, y, gx, gy] / 2 (solo.py:337-340)
+    assert (goals.abs() >= 1.0 - 1e-5).all() and (goals.abs() <= r0 + 1.0 + 1e-5).all()
+    assert (goals.abs() > r0).any()                                   # the larger radius is in use
+    envs.close()
