@@ -124,3 +124,36 @@ def test_config_mapping_matches_reference_defaults():
         abi.params_from_config({"model_urdf": "solo8", "mode": "headless"}, m)     # episode_length is required
     with pytest.raises(NotImplementedError):
         abi.params_from_config(make_config("solo8", flat_ground=False), m)
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every struct of include/solo_b200.h as gcc lays them out, against the ctypes
+    mirrors in solorl_b200/abi.py (a reordered or retyped field would silently corrupt the call)."""
+    structs = {"SoloModelTable": abi.SoloModelTable, "SoloSimParams": abi.SoloSimParams,
+               "SoloEpisodeStats": abi.SoloEpisodeStats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
+    for sname, cls in structs.items():
+        lines.append(f'  printf("{sname} sizeof %zu\\n", sizeof({sname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{sname} {fname} %zu\\n", offsetof({sname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)]).decode().split("\n")
+    seen = 0
+    for l in out:
+        if not l.strip():
+            continue
+        sname, fname, val = l.split()
+        cls = structs[sname]
+        if fname == "sizeof":
+            assert C.sizeof(cls) == int(val), sname
+        else:
+            assert getattr(cls, fname).offset == int(val), (sname, fname)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
+    assert abi.EPISODE_STATS_DTYPE.itemsize == C.sizeof(abi.SoloEpisodeStats)
+    for fname, _ in abi.SoloEpisodeStats._fields_:
+        assert abi.EPISODE_STATS_DTYPE.fields[fname][1] == getattr(abi.SoloEpisodeStats, fname).offset
