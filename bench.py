@@ -210,6 +210,34 @@ def time_policy_rollout(cfg, n, dev, rank, world, barrier, T=32, reps=10):
             "what": "policy act + env step + rollout-buffer append per step, device resident"}
 
 
+def time_saturated(cfg, dev, n, steps=60):
+    """Device-resident env-steps/s of the same workload at a batch that fills the GPU (several resident waves
+    of the 16-warps-per-SM throughput build), with the work counters of that run."""
+    import torch
+    from solorl_b200.envs import SoloVecEnv
+    env = SoloVecEnv(cfg, n, device=dev, seed=3)
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(7)
+    acts = [torch.rand(n, env.sim.act_dim, device=dev, generator=g) * 2 - 1 for _ in range(4)]
+    ncs, sws = [], []
+    for i in range(12):
+        env.sim.step(acts[i % 4])
+        w = env.sim.get_work_counters().float().mean(0)
+        ncs.append(w[0].item()); sws.append(w[1].item())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        env.sim.step(acts[i % 4])          # state (n x 0.8 KB = 52 MB at 65536 envs) + obs exceed what L2 keeps hot
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    nj = env.sim.nj
+    env.close()
+    return {"envs": n, "value": n / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms, "step_kernel_build": "throughput",
+            "flops_per_env_step": algorithmic_flops_per_env_step(nj, float(np.mean(ncs)), float(np.mean(sws)))}
+
+
 def run_ours(args):
     import torch
     from solorl_b200 import _lib, build
@@ -317,6 +345,15 @@ def run_ours(args):
         except Exception as e:      # the headline metric does not depend on it
             policy_rollout = {"error": repr(e)[:200]}
 
+    # ---- the same kernel when the batch fills the machine (throughput build, 65536 envs): how far the code is
+    #      from the FP32 peak once it is no longer limited by the 4096-env batch of the headline workload ------
+    saturated = None
+    if not args.no_saturated and world == 1:
+        try:
+            saturated = time_saturated(cfg, dev, args.saturated_envs)
+        except Exception as e:
+            saturated = {"error": repr(e)[:200]}
+
     if rank != 0:
         env.close()
         return
@@ -374,7 +411,11 @@ def run_ours(args):
         "roofline": roofline,
         "back_to_back_ms_per_step": b2b_ms, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "policy_rollout": policy_rollout,
+        "saturated": saturated,
     }
+    if saturated and "flops_per_env_step" in saturated:
+        ach = saturated["flops_per_env_step"] * saturated["value"] / 1e12
+        saturated.update({"achieved_tflops": ach, "peak_tflops": peak, "frac": ach / peak})
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     print(json.dumps(line), flush=True)
@@ -392,6 +433,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-policy-rollout", action="store_true")
+    ap.add_argument("--no-saturated", action="store_true")
+    ap.add_argument("--saturated-envs", type=int, default=65536)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
