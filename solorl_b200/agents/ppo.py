@@ -69,7 +69,7 @@ def broadcast_parameters(module, src=0):
 
 class PPO:
     def __init__(self, actor_critic, clip_param, ppo_epoch, mini_batch_size, value_loss_coef, entropy_coef,
-                 lr=None, l2_coef=0.0, max_grad_norm=None, use_clipped_value_loss=True):
+                 lr=None, l2_coef=0.0, max_grad_norm=None, use_clipped_value_loss=True, use_graph=True):
         self.actor_critic = actor_critic
         self.clip_param = clip_param
         self.ppo_epoch = ppo_epoch
@@ -79,34 +79,102 @@ class PPO:
         self.max_grad_norm = max_grad_norm
         self.use_clipped_value_loss = use_clipped_value_loss
         p0 = next(actor_critic.parameters())
-        # fused Adam: one multi-tensor launch instead of ~10 per parameter tensor (same arithmetic)
-        self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, weight_decay=l2_coef, fused=bool(p0.is_cuda))
+        self.use_graph = bool(use_graph and p0.is_cuda)
+        if p0.is_cuda:
+            # fused Adam: one multi-tensor launch instead of ~10 per parameter tensor (same arithmetic); capturable
+            # with a tensor learning rate so that the mini-batch step can be replayed as a CUDA graph while the
+            # linear schedule keeps changing the rate in place
+            self.optimizer = optim.Adam(actor_critic.parameters(), lr=torch.tensor(float(lr), device=p0.device),
+                                        weight_decay=l2_coef, fused=True, capturable=True)
+        else:
+            self.optimizer = optim.Adam(actor_critic.parameters(), lr=lr, weight_decay=l2_coef)
         self.grad_sync = FlatGradAllReduce(actor_critic.parameters())
+        self._graph = None
+        self._graph_key = None
+        self._warm = 0
+
+    # ---- one mini-batch step (ppo.py:47-81) on given batch tensors ----------------------------------------
+    def _step(self, obs, actions, old_values, returns, old_logp, adv_b, sums):
+        values, logp, entropy = self.actor_critic.evaluate_actions(obs, actions)
+        ratio = torch.exp(logp - old_logp)
+        surr = torch.min(ratio * adv_b, ratio.clamp(1.0 - self.clip_param, 1.0 + self.clip_param) * adv_b)
+        action_loss = -surr.mean()
+        if self.use_clipped_value_loss:
+            clipped = old_values + (values - old_values).clamp(-self.clip_param, self.clip_param)
+            value_loss = 0.5 * torch.max((values - returns).pow(2), (clipped - returns).pow(2)).mean()
+        else:
+            value_loss = 0.5 * (returns - values).pow(2).mean()
+        self.optimizer.zero_grad(set_to_none=False)
+        (value_loss * self.value_loss_coef + action_loss - entropy * self.entropy_coef).backward()
+        self.grad_sync()
+        nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
+        self.optimizer.step()
+        sums += torch.stack([value_loss.detach(), action_loss.detach(), entropy.detach()])
 
     def update(self, storage):
         adv = storage.returns[:-1] - storage.value_preds[:-1]
         mean, std = global_mean_std(adv)
         adv = (adv - mean) / (std + 1e-5)
+        if self.use_graph and adv.is_cuda and not dist_ready():
+            return self._update_graphed(storage, adv)
         sums = torch.zeros(3, device=adv.device)
         n_updates = 0
         for _ in range(self.ppo_epoch):
             for obs, actions, old_values, returns, _masks, old_logp, adv_b in \
                     storage.batch_generator(adv, self.mini_batch_size):
-                values, logp, entropy = self.actor_critic.evaluate_actions(obs, actions)
-                ratio = torch.exp(logp - old_logp)
-                surr = torch.min(ratio * adv_b, ratio.clamp(1.0 - self.clip_param, 1.0 + self.clip_param) * adv_b)
-                action_loss = -surr.mean()
-                if self.use_clipped_value_loss:
-                    clipped = old_values + (values - old_values).clamp(-self.clip_param, self.clip_param)
-                    value_loss = 0.5 * torch.max((values - returns).pow(2), (clipped - returns).pow(2)).mean()
-                else:
-                    value_loss = 0.5 * (returns - values).pow(2).mean()
-                self.optimizer.zero_grad(set_to_none=False)
-                (value_loss * self.value_loss_coef + action_loss - entropy * self.entropy_coef).backward()
-                self.grad_sync()
-                nn.utils.clip_grad_norm_(self.actor_critic.parameters(), self.max_grad_norm)
-                self.optimizer.step()
-                sums += torch.stack([value_loss.detach(), action_loss.detach(), entropy.detach()])
+                self._step(obs, actions, old_values, returns, old_logp, adv_b, sums)
                 n_updates += 1
         v, a, e = (sums / max(n_updates, 1)).tolist()      # one host sync per update, not per mini-batch
+        return v, a, e
+
+    # ---- the same loop with the mini-batch step replayed as ONE CUDA graph (single process) -----------------
+    def _update_graphed(self, storage, adv):
+        """~100 small launches per mini-batch step (two 3-layer MLPs forward and backward, losses, gradient clip,
+        Adam) cost more CPU time than GPU time; captured once, a step is one graph launch.  The batch is
+        selected by an index tensor that is overwritten before every replay (random mini-batches without
+        replacement, last partial batch dropped: storage.py:57-71)."""
+        ns, mb, dev = storage.num_samples, self.mini_batch_size, adv.device
+        key = (id(storage), ns, mb)
+        if self._graph_key != key:
+            self._graph, self._graph_key, self._warm = None, key, 0
+            self._idx = torch.zeros(mb, dtype=torch.long, device=dev)
+            self._adv = torch.zeros(ns, 1, device=dev)
+            self._sums = torch.zeros(3, device=dev)
+            self._flat = (storage.obs[:-1].reshape(ns, *storage.obs.shape[2:]), storage.actions.reshape(ns, -1),
+                          storage.value_preds[:-1].reshape(ns, 1), storage.returns[:-1].reshape(ns, 1),
+                          storage.action_log_probs.reshape(ns, 1))
+        self._adv.copy_(adv.reshape(ns, 1))
+        self._sums.zero_()
+
+        def body():
+            o, a, v, r, lp = (t.index_select(0, self._idx) for t in self._flat)
+            self._step(o, a, v, r, lp, self._adv.index_select(0, self._idx), self._sums)
+
+        n_updates = 0
+        for _ in range(self.ppo_epoch):
+            perm = torch.randperm(ns, device=dev)
+            for start in range(0, ns - mb + 1, mb):
+                self._idx.copy_(perm[start:start + mb])
+                if self._graph is not None:
+                    self._graph.replay()
+                elif self._warm < 3:                       # eager warm-up steps (they are real updates) on a side stream
+                    s = torch.cuda.Stream()
+                    s.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(s):
+                        body()
+                    torch.cuda.current_stream().wait_stream(s)
+                    self._warm += 1
+                else:
+                    try:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            body()
+                        self._graph = g
+                        g.replay()
+                    except Exception as e:                 # pragma: no cover - capture is best effort
+                        print(f"[ppo] CUDA graph capture of the update failed ({e}); continuing eagerly", flush=True)
+                        self.use_graph = False
+                        body()
+                n_updates += 1
+        v, a, e = (self._sums / max(n_updates, 1)).tolist()
         return v, a, e

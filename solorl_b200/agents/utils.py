@@ -17,7 +17,10 @@ def update_linear_schedule(optimizer, epoch, total_num_epochs, initial_lr):
     """lr = lr0 * (1 - epoch/total) (agents/utils.py:14-18)."""
     lr = initial_lr * (1.0 - epoch / float(total_num_epochs))
     for group in optimizer.param_groups:
-        group["lr"] = lr
+        if hasattr(group["lr"], "fill_"):      # tensor learning rate of a capturable optimizer: keep the tensor
+            group["lr"].fill_(lr)
+        else:
+            group["lr"] = lr
 
 
 def init_logging(logdir):

@@ -147,3 +147,39 @@ def test_fused_episode_accumulator_matches_host_records():
     assert st["return_min"] == tot["mn"] and st["return_max"] == tot["mx"] and st["length_max"] == tot["lmx"]
     assert tr.fetch()["episodes"] == 0
     env.close()
+
+
+def test_graphed_ppo_update_matches_eager():
+    """The mini-batch step replayed as a CUDA graph takes the same optimisation steps as the eager loop
+    (same random mini-batches, same Adam state): weights agree after three updates, the second and third of
+    which run almost entirely from the graph."""
+    import copy
+    from solorl_b200.agents.policy import Policy
+    from solorl_b200.agents.ppo import PPO
+    from solorl_b200.agents.storage import OPBuffer
+    from solorl_b200.agents.utils import update_linear_schedule
+    from solorl_b200.envs import Box
+    torch.manual_seed(0)
+    T, N, D, A = 8, 64, 20, 6
+    ac1 = Policy((D,), Box(-np.ones(A), np.ones(A)), None, {"hidden_size": 32}).cuda()
+    ac2 = copy.deepcopy(ac1)
+    agents = [PPO(ac1, 0.1, 3, 128, 0.5, 0.01, lr=1e-3, max_grad_norm=0.5, use_graph=True),
+              PPO(ac2, 0.1, 3, 128, 0.5, 0.01, lr=1e-3, max_grad_norm=0.5, use_graph=False)]
+    bufs = [OPBuffer(T, N, (D,), A, "cuda") for _ in range(2)]
+    for it in range(3):
+        g = torch.Generator(device="cuda").manual_seed(100 + it)
+        data = {k: torch.randn(*getattr(bufs[0], k).shape, device="cuda", generator=g)
+                for k in ("obs", "actions", "value_preds", "returns")}
+        with torch.no_grad():
+            _, lp, _ = ac2.evaluate_actions(data["obs"][:-1].reshape(-1, D), data["actions"].reshape(-1, A))
+        for agent, buf in zip(agents, bufs):
+            for k, v in data.items():
+                getattr(buf, k).copy_(v)
+            buf.action_log_probs.copy_(lp.reshape(T, N, 1))
+            update_linear_schedule(agent.optimizer, it, 5, 1e-3)
+            torch.manual_seed(7 + it)                      # same randperm sequence for both
+            losses = agent.update(buf)
+            assert np.isfinite(losses).all()
+        assert agents[0]._graph is not None or it == 0
+        for p1, p2 in zip(ac1.parameters(), ac2.parameters()):
+            assert torch.allclose(p1, p2, atol=2e-6), it
