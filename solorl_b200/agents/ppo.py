@@ -92,6 +92,10 @@ class PPO:
         self._graph = None
         self._graph_key = None
         self._warm = 0
+        # multi-GPU: the gradient all-reduce is captured inside the graph (NCCL collectives are capturable);
+        # SOLO_PPO_GRAPH_NCCL=0 keeps the multi-GPU update eager
+        import os
+        self.graph_with_nccl = os.environ.get("SOLO_PPO_GRAPH_NCCL", "1") != "0"
 
     # ---- one mini-batch step (ppo.py:47-81) on given batch tensors ----------------------------------------
     def _step(self, obs, actions, old_values, returns, old_logp, adv_b, sums):
@@ -115,7 +119,7 @@ class PPO:
         adv = storage.returns[:-1] - storage.value_preds[:-1]
         mean, std = global_mean_std(adv)
         adv = (adv - mean) / (std + 1e-5)
-        if self.use_graph and adv.is_cuda and not dist_ready():
+        if self.use_graph and adv.is_cuda and (not dist_ready() or self.graph_with_nccl):
             return self._update_graphed(storage, adv)
         sums = torch.zeros(3, device=adv.device)
         n_updates = 0
