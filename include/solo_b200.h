@@ -138,6 +138,15 @@ typedef struct SoloSimParams {
   double fall_z;             /* 0.05 (baseEnv.py:169) */
   double stand_z;            /* 0.2 (baseEnv.py:96) */
   int32_t reset_mode;        /* SOLO_RESET_* */
+  /* joint-limit rows: [3P] PyBullet's URDF importer adds a btMultiBodyJointLimitConstraint per revolute joint
+   * with lower <= upper (here +-joint_state_limit, solo.urdf:47); while q is beyond a limit the solver gets a
+   * unilateral row on that joint, swept before the contact normals */
+  int32_t joint_limits;           /* 1: on (reference behaviour); 0: joints are unlimited */
+  int32_t limit_rows_per_leg;     /* 1: at most one row per leg, the most violated joint (what the kernels
+                                   * solve); 0: one row per violated joint (Bullet; oracle only) */
+  double joint_limit_erp;         /* 0.2   btContactSolverInfo::m_erp */
+  double joint_limit_max_impulse; /* 100   btMultiBodyConstraint m_maxAppliedImpulse default */
+  double split_impulse_threshold; /* -0.04 violations deeper than this get no positional correction */
 } SoloSimParams;
 
 /* Per-env episode record, valid for envs whose `done` was 1 at the last step

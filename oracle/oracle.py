@@ -57,7 +57,7 @@ def lib():
                                         C.c_uint64, C.c_int64]
         L.oracle_env_destroy.argtypes = [vp]
         for f in ("oracle_nj", "oracle_act_dim", "oracle_obs_dim0", "oracle_obs_dim",
-                  "oracle_settle_count_last", "oracle_last_solver_iters"):
+                  "oracle_settle_count_last", "oracle_last_solver_iters", "oracle_last_limit_rows"):
             getattr(L, f).argtypes = [vp]
             getattr(L, f).restype = C.c_int
         L.oracle_env_reset.argtypes = [vp, dp]
@@ -179,6 +179,10 @@ class OracleEnv:
     @property
     def last_solver_iters(self):
         return self.L.oracle_last_solver_iters(self.h)
+
+    @property
+    def last_limit_rows(self):
+        return self.L.oracle_last_limit_rows(self.h)
 
     def action_to_torque(self, action):
         a = np.ascontiguousarray(action, dtype=np.float64)

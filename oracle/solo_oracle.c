@@ -204,6 +204,7 @@ struct OracleEnv {
   uint64_t seed; int64_t env_id; uint32_t episode, draw;
   int settle_last;
   int last_iters;        /* PGS iterations used by the last substep with contacts */
+  int last_limit_rows;   /* joint-limit rows of the last substep */
 };
 
 /* per-step workspace of the articulated-body algorithm, Bullet-style: every spatial
@@ -255,6 +256,11 @@ void oracle_default_params(SoloSimParams* p) {
   p->fall_z = 0.05;               /* baseEnv.py:169 */
   p->stand_z = 0.2;               /* baseEnv.py:96 */
   p->reset_mode = SOLO_RESET_CACHED;
+  p->joint_limits = 1;
+  p->limit_rows_per_leg = 1;
+  p->joint_limit_erp = 0.2;
+  p->joint_limit_max_impulse = 100.0;
+  p->split_impulse_threshold = -0.04;
 }
 
 OracleEnv* oracle_env_create(const SoloModelTable* m, const SoloSimParams* p, uint64_t seed,
@@ -285,6 +291,7 @@ int oracle_obs_dim0(const OracleEnv* e) { return e->d0; }
 int oracle_obs_dim(const OracleEnv* e) { return e->d; }
 int oracle_settle_count_last(const OracleEnv* e) { return e->settle_last; }
 int oracle_last_solver_iters(const OracleEnv* e) { return e->last_iters; }
+int oracle_last_limit_rows(const OracleEnv* e) { return e->last_limit_rows; }
 
 static void env_rng(OracleEnv* e, uint32_t w[4]) {
   w[0] = (uint32_t)((uint64_t)e->env_id & 0xffffffffu);
@@ -473,15 +480,17 @@ static void aba_forward(const OracleEnv* e, AbaWork* W, const double* tau, doubl
 /* Velocity response M^-1 J^T to a unit impulse `dir` (world) applied at world point `pt`
  * on link `link` ([3P] btMultiBody::calcAccelerationDeltasMultiDof); uses the articulated
  * inertias cached by the last aba_forward.  out[6+nj] = (dw world, dv world, dqd). */
+/* velocity response (angular, linear, joints) to a unit impulse along `dir` at world point `pt` of `link`
+ * (link < 0: none) plus a generalized impulse `jimp` on the joint of `jlink` (jlink < 0: none) */
 static void impulse_response(const OracleEnv* e, const AbaWork* W, int link, const v3 pt,
-                             const v3 dir, double* out) {
+                             const v3 dir, int jlink, double jimp, double* out) {
   const SoloModelTable* m = &e->m;
   int n = m->num_links;
   v6 Zt[MAXL], Z0, at[MAXL], a0;
   double ut[MAXL];
   for (int i = 0; i < n; i++) v6zero(Zt[i]);
   v6zero(Z0);
-  {
+  if (link >= 0) {
     v3 arm, tq, fl, tl;
     for (int k = 0; k < 3; k++) arm[k] = pt[k] - W->pw[link][k];
     v3cross(tq, arm, dir);
@@ -494,7 +503,7 @@ static void impulse_response(const OracleEnv* e, const AbaWork* W, int link, con
     v6 pa;
     memcpy(pa, Zt[i], sizeof(v6));
     if (m->jtype[i] == SOLO_JOINT_REVOLUTE) {
-      ut[i] = -v6dot(W->S[i], Zt[i]);
+      ut[i] = -v6dot(W->S[i], Zt[i]) + (i == jlink ? jimp : 0.0);
       for (int k = 0; k < 6; k++) pa[k] += W->h[i][k] * (ut[i] / W->D[i]);
     } else ut[i] = 0;
     if (par < 0) m6Tmulv_add(Z0, W->X[i], pa);
@@ -615,12 +624,45 @@ void oracle_substep(OracleEnv* e, const double* tau) {
       nc++;
     }
   }
+  /* 1b joint-limit rows ([3P] btMultiBodyJointLimitConstraint::createConstraintRows): a row exists while the
+   * joint position (start of the step) is at or beyond a limit; row 0 = lower bound, row 1 = upper bound */
+  int nl = 0, llink[2 * MAXL];
+  double ldir[2 * MAXL], lpen[2 * MAXL];
+  if (p->joint_limits) {
+    const double lim = p->joint_state_limit;
+    for (int i = 0; i < m->num_links; i++) {
+      if (m->jtype[i] != SOLO_JOINT_REVOLUTE) continue;
+      const double pen_lo = e->q[i] + lim, pen_hi = lim - e->q[i];
+      if (!(pen_lo > 0)) { llink[nl] = i; ldir[nl] = 1.0; lpen[nl] = pen_lo; nl++; }
+      if (!(pen_hi > 0)) { llink[nl] = i; ldir[nl] = -1.0; lpen[nl] = pen_hi; nl++; }
+    }
+    if (p->limit_rows_per_leg == 1 && nl > 1) {
+      /* kernel-compatible restriction: one row per leg, the most violated joint (first on ties) */
+      int keep[2 * MAXL], nk = 0;
+      for (int a = 0; a < nl; a++) {
+        int ra = llink[a];
+        while (m->parent[ra] >= 0) ra = m->parent[ra];
+        int best = 1;
+        for (int b = 0; b < nl; b++) {
+          if (b == a) continue;
+          int rb = llink[b];
+          while (m->parent[rb] >= 0) rb = m->parent[rb];
+          if (rb != ra) continue;
+          if (lpen[b] < lpen[a] || (lpen[b] == lpen[a] && b < a)) best = 0;
+        }
+        if (best) keep[nk++] = a;
+      }
+      for (int a = 0; a < nk; a++) { llink[a] = llink[keep[a]]; ldir[a] = ldir[keep[a]]; lpen[a] = lpen[keep[a]]; }
+      nl = nk;
+    }
+  }
+  e->last_limit_rows = nl;
   /* 2 unconstrained velocity */
   for (int k = 0; k < 3; k++) { e->vang[k] += dt * qdd[k]; e->vlin[k] += dt * qdd[3 + k]; }
   for (int j = 0; j < e->nj; j++) e->qd[e->link_of_dof[j]] += dt * qdd[6 + j];
   clamp_velocities(e);
 
-  if (nc > 0) {
+  if (nc > 0 || nl > 0) {
     double vel[MAXD], dv[MAXD];
     for (int k = 0; k < 3; k++) { vel[k] = e->vang[k]; vel[3 + k] = e->vlin[k]; }
     for (int j = 0; j < e->nj; j++) vel[6 + j] = e->qd[e->link_of_dof[j]];
@@ -635,7 +677,7 @@ void oracle_substep(OracleEnv* e, const double* tau) {
       for (int r = 0; r < 3; r++) {
         Row* row = (r == 0) ? &rn[c] : &rf[c][r - 1];
         contact_jacobian(e, &W, l, cpt[c], dirs[r], row->J);
-        impulse_response(e, &W, l, cpt[c], dirs[r], row->u);
+        impulse_response(e, &W, l, cpt[c], dirs[r], -1, 0.0, row->u);
         double d = rowdot(nd, row->J, row->u);
         row->dinv = 1.0 / d;
         double rel_vel = rowdot(nd, row->J, vel);
@@ -650,6 +692,22 @@ void oracle_substep(OracleEnv* e, const double* tau) {
         row->lambda = 0; /* [3P] warm starting is disabled for multibody contacts */
       }
     }
+    Row rl[2 * MAXL];
+    for (int c = 0; c < nl; c++) {
+      Row* row = &rl[c];
+      const int dof = 6 + e->dof_of_link[llink[c]];
+      const v3 zero = {0, 0, 0};
+      for (int k = 0; k < nd; k++) row->J[k] = 0;
+      row->J[dof] = ldir[c];
+      impulse_response(e, &W, -1, zero, zero, llink[c], ldir[c], row->u);
+      row->dinv = 1.0 / rowdot(nd, row->J, row->u);
+      const double rel_vel = rowdot(nd, row->J, vel);
+      /* splitImpulse is on by default: shallow violations combine the ERP push-back with the velocity target,
+       * deeper ones put it into m_rhsPenetration, which the multibody solver never applies */
+      const double positional_error = (lpen[c] > p->split_impulse_threshold) ? -lpen[c] * p->joint_limit_erp / dt : 0.0;
+      row->rhs = (positional_error - rel_vel) * row->dinv;
+      row->lambda = 0;
+    }
     /* 4 PGS ([3P] btMultiBodyConstraintSolver::solveSingleIteration; the loop of
      * solveGroupCacheFriendlyIterations stops after the iteration whose largest squared row
      * residual, in velocity units deltaImpulse / jacDiagABInv, is <= the threshold) */
@@ -657,6 +715,29 @@ void oracle_substep(OracleEnv* e, const double* tau) {
     for (int it = 0; it < p->solver_iters; it++) {
       double res2 = 0;
       e->last_iters = it + 1;
+      /* non-contact rows come first in every iteration.  limit_rows_per_leg == 1 (what the kernels solve):
+       * the rows, one per leg at most, are relaxed as one simultaneous group (all candidates from the same
+       * state) -- identical to Bullet's sequential order when an env holds a single limit row; otherwise
+       * Bullet's order, row by row */
+      {
+        double dl[2 * MAXL];
+        const int simultaneous = (p->limit_rows_per_leg == 1);
+        for (int c = 0; c < nl; c++) {
+          Row* r = &rl[c];
+          double delta = r->rhs - rowdot(nd, r->J, dv) * r->dinv;
+          double sum = r->lambda + delta;
+          if (sum < 0) { delta = -r->lambda; r->lambda = 0; }
+          else if (sum > p->joint_limit_max_impulse) { delta = p->joint_limit_max_impulse - r->lambda; r->lambda = p->joint_limit_max_impulse; }
+          else r->lambda = sum;
+          dl[c] = delta;
+          if (!simultaneous) for (int k = 0; k < nd; k++) dv[k] += r->u[k] * delta;
+          double rv = delta / r->dinv;
+          if (rv * rv > res2) res2 = rv * rv;
+        }
+        if (simultaneous)
+          for (int c = 0; c < nl; c++)
+            for (int k = 0; k < nd; k++) dv[k] += rl[c].u[k] * dl[c];
+      }
       for (int c = 0; c < nc; c++) {
         Row* r = &rn[c];
         double delta = r->rhs - rowdot(nd, r->J, dv) * r->dinv;

@@ -68,6 +68,7 @@ void oracle_get_goal(const OracleEnv* e, double* gxy);
 void oracle_set_goal_radius(OracleEnv* e, double r);
 int oracle_settle_count_last(const OracleEnv* e);
 int oracle_last_solver_iters(const OracleEnv* e);
+int oracle_last_limit_rows(const OracleEnv* e);
 
 /* solo.py:224-259 + PD.py:3-10 on the env's current state; tau[nj] */
 void oracle_action_to_torque(const OracleEnv* e, const double* action, double* tau);

@@ -83,6 +83,11 @@ class SoloSimParams(C.Structure):
         ("fall_z", C.c_double),
         ("stand_z", C.c_double),
         ("reset_mode", C.c_int32),
+        ("joint_limits", C.c_int32),
+        ("limit_rows_per_leg", C.c_int32),
+        ("joint_limit_erp", C.c_double),
+        ("joint_limit_max_impulse", C.c_double),
+        ("split_impulse_threshold", C.c_double),
     ]
 
 
@@ -185,6 +190,11 @@ def default_params() -> SoloSimParams:
     p.fall_z = 0.05
     p.stand_z = 0.2
     p.reset_mode = RESET_CACHED
+    p.joint_limits = 1
+    p.limit_rows_per_leg = 1
+    p.joint_limit_erp = 0.2
+    p.joint_limit_max_impulse = 100.0
+    p.split_impulse_threshold = -0.04
     return p
 
 
@@ -222,11 +232,12 @@ def params_from_config(config: dict, model: Optional[SoloModel] = None) -> SoloS
     p.pointgoal_dt = p.frame_skip * p.dt
     if model is not None:
         p.joint_state_limit = model.joint_state_limit          # solo.py:109
-    for k in ("torque_hold", "solver_iters", "cone_friction"):
+    for k in ("torque_hold", "solver_iters", "cone_friction", "joint_limits", "limit_rows_per_leg"):
         if k in config:
             setattr(p, k, int(config[k]))
     for k in ("contact_erp", "contact_margin", "contact_slop", "friction", "lin_damping",
-              "ang_damping", "goal_radius", "solver_residual_threshold"):
+              "ang_damping", "goal_radius", "solver_residual_threshold", "joint_limit_erp",
+              "joint_limit_max_impulse", "split_impulse_threshold"):
         if k in config:
             setattr(p, k, float(config[k]))
     rm = config.get("reset_mode", "cached")

@@ -74,6 +74,9 @@ struct SimConst {
   int settle_min, settle_span;
   float goal_reach, inv_pg_dt, flag_force, fall_z, stand_z;
   int reset_mode;
+  /* joint-limit rows ([3P] btMultiBodyJointLimitConstraint) */
+  int joint_limits;
+  float lim_erp, lim_max_impulse, lim_split_thr;
 };
 
 /* ------------------------------------------------------------------ small helpers */
@@ -621,6 +624,73 @@ SOLO_HD void contact_setup(const LegConst& lc, const ModelConst& mc, const SimCo
   }
 }
 
+/* ------------------------------------------------------------------ joint-limit rows
+ * [3P] PyBullet's URDF importer gives every revolute joint with lower <= upper a
+ * btMultiBodyJointLimitConstraint; while the joint position is at or beyond a limit
+ * (createConstraintRows: `if (penetration > 0) continue;`) the solver holds a unilateral row on that joint,
+ * impulse in [0, maxAppliedImpulse], target velocity erp*|penetration|/dt (no positional part beyond the
+ * split-impulse threshold), relaxed BEFORE the contact normals in every sweep.  The kernels carry at most
+ * one such row per leg: the most violated joint (first on ties); SoloSimParams.limit_rows_per_leg = 1 makes
+ * the oracle do the same. */
+template <int NJL>
+struct LimitRow {
+  float U[NJL];          /* generalized force the unit row impulse puts on joint k of the leg (0 above the joint) */
+  float P[6], K[6];      /* base wrench per unit impulse, IA0^-1 P */
+  float b;               /* target relative velocity */
+  float LL;              /* leg-local diagonal term  sum_k U_k^2 invD_k */
+  float Lc[3];           /* leg-local coupling with the foot's contact rows  sum_k U_k sP_k[m] invD_k */
+  int active;
+};
+
+/* which joint of the leg, if any: dir = +1 at the lower bound, -1 at the upper, pen <= 0 */
+template <int NJL>
+SOLO_HD bool limit_select(const SimConst& sc, const Lane<NJL>& ln, int& kL, float& dir, float& pen) {
+  bool any = false;
+  kL = 0; dir = 0.f; pen = 0.f;
+  if (!sc.joint_limits) return false;
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    const float lo = ln.q[k] + sc.q_limit, hi = sc.q_limit - ln.q[k];
+    /* lower row first, then upper, in joint order; strictly-more-violated replaces */
+    if (!(lo > 0.f) && (!any || lo < pen)) { any = true; kL = k; dir = 1.f; pen = lo; }
+    if (!(hi > 0.f) && (!any || hi < pen)) { any = true; kL = k; dir = -1.f; pen = hi; }
+  }
+  return any;
+}
+
+/* Row data of the selected joint.  Same propagation as a contact row (contact_setup), with the unit impulse
+ * entering as a generalized force on joint kL instead of a wrench at the foot.  kL is a run-time value: every
+ * per-joint array is indexed by the unrolled k and selected with predicates, never by kL. */
+template <int NJL>
+SOLO_HD void limit_setup(const SimConst& sc, const BaseWork& bw, const Lane<NJL>& ln, bool any, int kL, float dir,
+                         float pen, LimitRow<NJL>& lr) {
+  float w[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float qdL = 0.f;
+  lr.LL = 0.f; lr.Lc[0] = lr.Lc[1] = lr.Lc[2] = 0.f;
+#pragma unroll
+  for (int k = NJL - 1; k >= 0; k--) {
+    const bool at = any && (k == kL);
+    float s = dot3(ln.ax[k], w) + (at ? dir : 0.f);       /* w is still zero above the joint */
+    s = (any && k <= kL) ? s : 0.f;
+    lr.U[k] = s;
+    qdL = at ? ln.qd[k] : qdL;
+    const float g = s * ln.invD[k];
+#pragma unroll
+    for (int i = 0; i < 6; i++) w[i] -= ln.h[k][i] * g;
+    cross3_add(ln.r[k], w + 3, w);                        /* moments about the parent's origin */
+    lr.LL += g * s;
+#pragma unroll
+    for (int m = 0; m < 3; m++) lr.Lc[m] += g * ln.sP[k][m];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) { lr.P[i] = w[i]; lr.K[i] = w[i]; }
+  ldl6_solve(bw.F, lr.K);
+  const float rel_vel = dir * qdL;
+  const float positional = (pen > sc.lim_split_thr) ? -pen * sc.lim_erp * sc.inv_dt : 0.f;
+  lr.b = positional - rel_vel;
+  lr.active = any ? 1 : 0;
+}
+
 /* Global row index of (foot i, direction m): normals first, then friction pairs
  * (the order btMultiBodyConstraintSolver sweeps them). */
 SOLO_HD constexpr int row_of(int foot, int m) { return m == 0 ? foot : 4 + 2 * foot + (m - 1); }
@@ -652,10 +722,16 @@ SOLO_HD void assemble_block(const Lane<NJL>& ln, int foot, int j, const float Kj
  * row onto [-mu lambda_n, mu lambda_n] when cone friction is off.  No warm start.  The sweep loop
  * ends after solver_iters iterations or once the largest squared velocity residual
  * (dlambda * A[r][r])^2 of an iteration is <= solver_residual_threshold. */
-struct PgsLane {
-  float B[3][kRows];
-  float g[3], lam[3], diag[3];
+template <int NR, int NC>
+struct PgsLaneT {
+  float B[NR][NC];
+  float g[NR], lam[NR], diag[NR];
 };
+typedef PgsLaneT<3, kRows> PgsLane;
+/* with joint-limit rows: a fourth row per lane (the leg's limit row), columns 12..15 = the four limit rows */
+constexpr int kRowsL = kRows + 4;
+typedef PgsLaneT<4, kRowsL> PgsLane4;
+SOLO_HD constexpr int limit_col(int leg) { return kRows + leg; }
 template <int NJL>
 SOLO_HD void pgs_lane_init(const Lane<NJL>& ln, int foot, float rows[3][kRows], unsigned active_mask,
                            PgsLane& pl) {
@@ -680,13 +756,15 @@ SOLO_HD void pgs_lane_init(const Lane<NJL>& ln, int foot, float rows[3][kRows], 
   }
 }
 /* candidate for this lane's normal row: new value, impulse change, velocity residual */
-SOLO_HD void pgs_normal_candidate(const PgsLane& pl, float& nv, float& d, float& rv) {
+template <class PL>
+SOLO_HD void pgs_normal_candidate(const PL& pl, float& nv, float& d, float& rv) {
   nv = fmaxf(pl.g[0], 0.f);
   d = nv - pl.lam[0];
   rv = d * pl.diag[0];
 }
 /* candidates for this lane's friction pair (cone) */
-SOLO_HD void pgs_cone_candidate(const PgsLane& pl, float mu, float& nA, float& nB, float& dA, float& dB,
+template <class PL>
+SOLO_HD void pgs_cone_candidate(const PL& pl, float mu, float& nA, float& nB, float& dA, float& dB,
                                 float& rv) {
   /* Bullet clamps sA to +-|lim sin(atan2(sA,sB))| and sB to +-|lim cos(.)|, i.e. it scales the pair
    * (sA,sB) back onto the circle of radius lim when it lies outside: (sA,sB) * min(1, lim/|s|).
@@ -703,7 +781,8 @@ SOLO_HD void pgs_cone_candidate(const PgsLane& pl, float mu, float& nA, float& n
   rv = dA * pl.diag[1] + dB * pl.diag[2];
 }
 /* candidate for one friction row (pyramid), q = 0/1 */
-SOLO_HD void pgs_pyramid_candidate(const PgsLane& pl, float mu, int q, float& nv, float& d, float& rv) {
+template <class PL>
+SOLO_HD void pgs_pyramid_candidate(const PL& pl, float mu, int q, float& nv, float& d, float& rv) {
   const float lim = mu * pl.lam[0];
   nv = clampf(pl.g[1 + q], -lim, lim);
   d = nv - pl.lam[1 + q];
@@ -713,6 +792,64 @@ SOLO_HD void pgs_pyramid_candidate(const PgsLane& pl, float mu, int q, float& nv
 SOLO_HD void pgs_apply(PgsLane& pl, int col, float d) {
 #pragma unroll
   for (int m = 0; m < 3; m++) pl.g[m] -= pl.B[m][col] * d;
+}
+SOLO_HD void pgs_apply(PgsLane4& pl, int col, float d) {
+#pragma unroll
+  for (int m = 0; m < 4; m++) pl.g[m] -= pl.B[m][col] * d;
+}
+/* candidate for this lane's joint-limit row: impulse in [0, max], otherwise like a normal row */
+SOLO_HD void pgs_limit_candidate(const PgsLane4& pl, float max_impulse, float& nv, float& d, float& rv) {
+  nv = fminf(fmaxf(pl.g[3], 0.f), max_impulse);
+  d = nv - pl.lam[3];
+  rv = d * pl.diag[3];
+}
+
+/* Four-row versions of assemble_block / pgs_lane_init: row 3 / column 12+j is the limit row of leg j.
+ * Kj[n] (n < 3) and KLj are K of the contact rows and of the limit row of lane j. */
+template <int NJL>
+SOLO_HD void assemble_block4(const Lane<NJL>& ln, const LimitRow<NJL>& lr, int foot, int j, const float Kj[3][6],
+                             const float* KLj, bool limit_col_on, float rows[4][kRowsL]) {
+  const bool own = (j == foot);
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+#pragma unroll
+    for (int n = 0; n < 3; n++) rows[m][row_of(j, n)] = dot6(ln.P[m], Kj[n]) + (own ? ln.Lm[sym3_idx(m, n)] : 0.f);
+  }
+#pragma unroll
+  for (int n = 0; n < 3; n++) rows[3][row_of(j, n)] = dot6(lr.P, Kj[n]) + (own ? lr.Lc[n] : 0.f);
+  if (limit_col_on) {   /* uniform: some env of the warp has a limit row on leg j */
+#pragma unroll
+    for (int m = 0; m < 3; m++) rows[m][limit_col(j)] = dot6(ln.P[m], KLj) + (own ? lr.Lc[m] : 0.f);
+    rows[3][limit_col(j)] = dot6(lr.P, KLj) + (own ? lr.LL : 0.f);
+  } else {
+#pragma unroll
+    for (int m = 0; m < 4; m++) rows[m][limit_col(j)] = 0.f;
+  }
+}
+template <int NJL>
+SOLO_HD void pgs_lane_init4(const Lane<NJL>& ln, const LimitRow<NJL>& lr, int foot, float rows[4][kRowsL],
+                            unsigned active_mask, unsigned limit_mask, PgsLane4& pl) {
+#pragma unroll
+  for (int m = 0; m < 4; m++) {
+    const bool row_on = (m < 3) ? (ln.active != 0) : (lr.active != 0);
+    float d = 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) d = (j == foot) ? rows[m][m < 3 ? row_of(j, m) : limit_col(j)] : d;
+    const float invd = row_on ? solo_rcp(d) : 0.f;
+    pl.diag[m] = row_on ? d : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+#pragma unroll
+      for (int n = 0; n < 4; n++) {
+        const int c = (n < 3) ? row_of(j, n) : limit_col(j);
+        const bool col_on = (n < 3) ? (((active_mask >> j) & 1u) != 0) : (((limit_mask >> j) & 1u) != 0);
+        const bool own_diag = (j == foot) && (n == m);
+        pl.B[m][c] = (col_on && !own_diag) ? rows[m][c] * invd : 0.f;
+      }
+    }
+    pl.g[m] = ((m < 3) ? ln.b[m] : lr.b) * invd;
+    pl.lam[m] = 0.f;
+  }
 }
 
 /* Wrench on the base produced by this foot's impulses, already multiplied by IA0^-1:
@@ -780,6 +917,29 @@ SOLO_HD void leg_foot_center(const LegConst& lc, const float* q, float* out) {
 SOLO_HD float actuator_torque(const SimConst& sc, float q, float qd, float q_des, float v_des, float P, float D,
                               float tau_ff) {
   return clampf(P * (q_des - q) + D * (v_des - qd) + tau_ff, -sc.max_torque, sc.max_torque);
+}
+
+/* the same two steps when the leg also carries a joint-limit impulse lamL */
+template <int NJL>
+SOLO_HD void impulse_base_part4(const Lane<NJL>& ln, const LimitRow<NJL>& lr, const float* lam4, float* dv0_part) {
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+    dv0_part[i] = ln.K[0][i] * lam4[0] + ln.K[1][i] * lam4[1] + ln.K[2][i] * lam4[2] + lr.K[i] * lam4[3];
+}
+template <int NJL>
+SOLO_HD void impulse_leg4(Lane<NJL>& ln, const LimitRow<NJL>& lr, const SimConst& sc, const float* lam4,
+                          const float* dv0) {
+  float a[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) a[i] = dv0[i];
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    cross3_add(a, ln.r[k], a + 3);
+    float us = ln.sP[k][0] * lam4[0] + ln.sP[k][1] * lam4[1] + ln.sP[k][2] * lam4[2] + lr.U[k] * lam4[3];
+    float dq = (us - dot6(ln.h[k], a)) * ln.invD[k];
+    a[0] += ln.ax[k][0] * dq; a[1] += ln.ax[k][1] * dq; a[2] += ln.ax[k][2] * dq;
+    ln.qd[k] = clampf(ln.qd[k] + dq, -sc.vmax, sc.vmax);
+  }
 }
 
 /* Semi-implicit Euler position update ([3P] btMultiBody::stepPositionsMultiDof). */

@@ -116,6 +116,9 @@ inline int build_sim_const(const SoloSimParams& p, SimConst& sc, std::string& er
   sc.goal_reach = (float)p.goal_reach_dist; sc.inv_pg_dt = (float)(1.0 / p.pointgoal_dt);
   sc.flag_force = (float)p.contact_flag_force; sc.fall_z = (float)p.fall_z; sc.stand_z = (float)p.stand_z;
   sc.reset_mode = p.reset_mode;
+  sc.joint_limits = p.joint_limits ? 1 : 0;
+  sc.lim_erp = (float)p.joint_limit_erp; sc.lim_max_impulse = (float)p.joint_limit_max_impulse;
+  sc.lim_split_thr = (float)p.split_impulse_threshold;
   return SOLO_OK;
 }
 
@@ -133,6 +136,11 @@ inline void fill_default_params(SoloSimParams* p) {
   p->goal_radius = 2.0; p->goal_reach_dist = 0.5; p->pointgoal_dt = 4.0 / 240.0;
   p->contact_flag_force = 0.2; p->fall_z = 0.05; p->stand_z = 0.2;
   p->reset_mode = SOLO_RESET_CACHED;
+  p->joint_limits = 1;
+  p->limit_rows_per_leg = 1;
+  p->joint_limit_erp = 0.2;
+  p->joint_limit_max_impulse = 100.0;
+  p->split_impulse_threshold = -0.04;
 }
 
 }  // namespace solo

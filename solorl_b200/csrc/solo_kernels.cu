@@ -327,6 +327,69 @@ __device__ __forceinline__ void pgs_sweeps(PgsLane& pl, const SimConst& sc, int 
   }
 }
 
+/* The sweep loop when some env of the warp holds a joint-limit row: a fourth row per lane, relaxed first in
+ * every sweep like Bullet's non-contact rows (under random actions 11 % of env steps hold a limit row). */
+template <bool CONE>
+__device__ __forceinline__ void pgs_sweeps4(PgsLane4& pl, const SimConst& sc, int leg, unsigned gbase, unsigned amask,
+                                            unsigned lmask, unsigned lwarp, int nc, float* lam4, int& sweep_feet) {
+  const unsigned kFull = 0xffffffffu;
+  bool conv = (amask == 0) && (lmask == 0);
+  lam4[0] = lam4[1] = lam4[2] = lam4[3] = 0.f;
+  for (int it = 0; it < sc.iters; it++) {
+    float res_own = 0.f;
+    sweep_feet += conv ? 0 : nc;
+    {
+      /* the (at most four) limit rows of an env belong to different legs and are relaxed as ONE group: every
+       * lane takes its candidate from the same state, the four changes are exchanged in one shuffle round.
+       * With a single limit row per env (99.5 % of the cases under random actions) this IS Bullet's
+       * sequential order; with several it is a Jacobi step among rows that couple only through the base. */
+      float nv, d, rv;
+      pgs_limit_candidate(pl, sc.lim_max_impulse, nv, d, rv);
+      pl.lam[3] = nv;
+      res_own = fmaxf(res_own, fabsf(rv));
+      const float d0 = __shfl_sync(kFull, d, gbase + 0), d1 = __shfl_sync(kFull, d, gbase + 1);
+      const float d2 = __shfl_sync(kFull, d, gbase + 2), d3 = __shfl_sync(kFull, d, gbase + 3);
+      pgs_apply(pl, limit_col(0), d0);
+      pgs_apply(pl, limit_col(1), d1);
+      pgs_apply(pl, limit_col(2), d2);
+      pgs_apply(pl, limit_col(3), d3);
+    }
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      float nv, d, rv;
+      pgs_normal_candidate(pl, nv, d, rv);
+      const float db = __shfl_sync(kFull, d, gbase + f);
+      if (leg == f) { pl.lam[0] = nv; res_own = fmaxf(res_own, fabsf(rv)); }
+      pgs_apply(pl, row_of(f, 0), db);
+    }
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+      if (CONE) {
+        float nA, nB, dA, dB, rv;
+        pgs_cone_candidate(pl, sc.mu, nA, nB, dA, dB, rv);
+        const float dAb = __shfl_sync(kFull, dA, gbase + f);
+        const float dBb = __shfl_sync(kFull, dB, gbase + f);
+        if (leg == f) { pl.lam[1] = nA; pl.lam[2] = nB; res_own = fmaxf(res_own, fabsf(rv)); }
+        pgs_apply(pl, row_of(f, 1), dAb);
+        pgs_apply(pl, row_of(f, 2), dBb);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          float nv, d, rv;
+          pgs_pyramid_candidate(pl, sc.mu, q, nv, d, rv);
+          const float db = __shfl_sync(kFull, d, gbase + f);
+          if (leg == f) { pl.lam[1 + q] = nv; res_own = fmaxf(res_own, fabsf(rv)); }
+          pgs_apply(pl, row_of(f, 1 + q), db);
+        }
+      }
+    }
+    if (!conv) { lam4[0] = pl.lam[0]; lam4[1] = pl.lam[1]; lam4[2] = pl.lam[2]; lam4[3] = pl.lam[3]; }
+    const unsigned okb = __ballot_sync(kFull, conv || (res_own * res_own <= sc.res_thr));
+    conv = conv || (((okb >> gbase) & 0xFu) == 0xFu);
+    if (okb == kFull) break;
+  }
+}
+
 /* One Bullet-equivalent substep for the four lanes of an env (see solo_core.cuh).
  * Control flow is kept WARP-uniform (skip masks and the sweep-loop exit are warp votes, envs that
  * have nothing to do contribute exact zeros) so that every shuffle is a full-mask shuffle of a
@@ -360,8 +423,52 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
   const unsigned amask = (ball >> gbase) & 0xFu;                 /* feet in contact of this env */
   const unsigned wmask = (ball | (ball >> 4) | (ball >> 8) | (ball >> 12) | (ball >> 16) | (ball >> 20) |
                           (ball >> 24) | (ball >> 28)) & 0xFu;     /* ... of any env of the warp */
+  /* joint-limit rows (positions of the start of the substep, velocities after the unconstrained update) */
+  int kL;
+  float dirL, penL;
+  const bool lim_any = limit_select<NJL>(sc, ln, kL, dirL, penL);
+  const unsigned lball = __ballot_sync(kFull, lim_any);
+  const unsigned lmask = (lball >> gbase) & 0xFu;
+  const unsigned lwarp = (lball | (lball >> 4) | (lball >> 8) | (lball >> 12) | (lball >> 16) | (lball >> 20) |
+                          (lball >> 24) | (lball >> 28)) & 0xFu;
   float lam3[3] = {0.f, 0.f, 0.f};
-  if (wmask) {   /* warp-uniform */
+  if (lwarp) {   /* warp-uniform: some env of the warp holds a joint-limit row -> four rows per lane */
+    LimitRow<NJL> lr;
+    limit_setup<NJL>(sc, bw, ln, lim_any, kL, dirL, penL, lr);
+    PgsLane4 pl;
+    {
+      float rows[4][kRowsL];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float Kj[3][6], KLj[6];
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) Kj[n][i] = __shfl_sync(kFull, ln.K[n][i], gbase + j);
+        }
+        const bool col_on = ((lwarp >> j) & 1u) != 0;   /* warp-uniform */
+#pragma unroll
+        for (int i = 0; i < 6; i++) KLj[i] = col_on ? __shfl_sync(kFull, lr.K[i], gbase + j) : 0.f;
+        assemble_block4<NJL>(ln, lr, leg, j, Kj, KLj, col_on, rows);
+      }
+      pgs_lane_init4<NJL>(ln, lr, leg, rows, amask, lmask, pl);
+    }
+    const int nc = __popc(amask);
+    nc_sum += nc;
+    float lam4[4];
+    if (sc.cone) pgs_sweeps4<true>(pl, sc, leg, gbase, amask, lmask, lwarp, nc, lam4, sweep_feet);
+    else pgs_sweeps4<false>(pl, sc, leg, gbase, amask, lmask, lwarp, nc, lam4, sweep_feet);
+    lam3[0] = lam4[0]; lam3[1] = lam4[1]; lam3[2] = lam4[2];
+    float part[6], dv0[6];
+    impulse_base_part4<NJL>(ln, lr, lam4, part);
+#pragma unroll
+    for (int i = 0; i < 6; i++) dv0[i] = sum4(part[i]);
+    impulse_leg4<NJL>(ln, lr, sc, lam4, dv0);
+    float dw[3], dvl[3];
+    mat3_mulv(bw.R, dv0, dw);
+    mat3_mulv(bw.R, dv0 + 3, dvl);
+    base_add_velocity(sc, st, dw, dvl, 1.0f);
+  } else if (wmask) {   /* warp-uniform */
     PgsLane pl;
     {
       float rows[3][kRows];
@@ -1076,6 +1183,9 @@ int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_
   int rc = build_model_const(*model, h->mc, err);
   if (rc == SOLO_OK) rc = build_sim_const(*params, h->sc, err);
   if (rc == SOLO_OK && params->num_history_stack > 8) { rc = SOLO_E_ARG; err = "num_history_stack > 8"; }
+  if (rc == SOLO_OK && params->joint_limits && params->limit_rows_per_leg != 1) {
+    rc = SOLO_E_ARG; err = "joint_limits: the kernels solve one limit row per leg (limit_rows_per_leg must be 1)";
+  }
   if (rc != SOLO_OK) { delete h; return fail(nullptr, rc, err); }
   h->n = num_envs; h->njl = h->mc.njl; h->nj = 4 * h->njl;
   h->A = h->nj + (params->control == SOLO_CONTROL_VPD ? 2 : 0);

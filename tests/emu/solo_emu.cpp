@@ -91,7 +91,69 @@ static void emu_substep(Emu* e, const float* tau) {
   }
   float lam[kRows];
   for (int r = 0; r < kRows; r++) lam[r] = 0.f;
-  if (mask) {
+  /* joint-limit rows: the four-row lane program (group_substep's `lwarp` branch) */
+  unsigned lmask = 0;
+  LimitRow<NJL> lr[4];
+  float lamL[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int l = 0; l < 4; l++) {
+    int kL; float dirL, penL;
+    const bool any = limit_select<NJL>(sc, ln[l], kL, dirL, penL);
+    limit_setup<NJL>(sc, bw, ln[l], any, kL, dirL, penL, lr[l]);
+    if (any) lmask |= 1u << l;
+  }
+  if (lmask) {
+    PgsLane4 pl[4];
+    for (int l = 0; l < 4; l++) {
+      float rows[4][kRowsL];
+      for (int j = 0; j < 4; j++) assemble_block4<NJL>(ln[l], lr[l], l, j, ln[j].K, lr[j].K, ((lmask >> j) & 1u) != 0, rows);
+      pgs_lane_init4<NJL>(ln[l], lr[l], l, rows, mask, lmask, pl[l]);
+    }
+    for (int it = 0; it < sc.iters; it++) {
+      float res2 = 0.f;
+      {   /* the limit rows of the four legs: one simultaneous group */
+        float dl[4];
+        for (int f = 0; f < 4; f++) {
+          float nv, rv;
+          pgs_limit_candidate(pl[f], sc.lim_max_impulse, nv, dl[f], rv);
+          pl[f].lam[3] = nv;
+          res2 = fmaxf(res2, rv * rv);
+        }
+        for (int f = 0; f < 4; f++)
+          for (int l = 0; l < 4; l++) pgs_apply(pl[l], limit_col(f), dl[f]);
+      }
+      for (int f = 0; f < 4; f++) {
+        if (!((mask >> f) & 1u)) continue;
+        float nv, d, rv;
+        pgs_normal_candidate(pl[f], nv, d, rv);
+        pl[f].lam[0] = nv;
+        for (int l = 0; l < 4; l++) pgs_apply(pl[l], row_of(f, 0), d);
+        res2 = fmaxf(res2, rv * rv);
+      }
+      for (int f = 0; f < 4; f++) {
+        if (!((mask >> f) & 1u)) continue;
+        if (sc.cone) {
+          float nA, nB, dA, dB, rv;
+          pgs_cone_candidate(pl[f], sc.mu, nA, nB, dA, dB, rv);
+          pl[f].lam[1] = nA; pl[f].lam[2] = nB;
+          for (int l = 0; l < 4; l++) { pgs_apply(pl[l], row_of(f, 1), dA); pgs_apply(pl[l], row_of(f, 2), dB); }
+          res2 = fmaxf(res2, rv * rv);
+        } else {
+          for (int q = 0; q < 2; q++) {
+            float nv, d, rv;
+            pgs_pyramid_candidate(pl[f], sc.mu, q, nv, d, rv);
+            pl[f].lam[1 + q] = nv;
+            for (int l = 0; l < 4; l++) pgs_apply(pl[l], row_of(f, 1 + q), d);
+            res2 = fmaxf(res2, rv * rv);
+          }
+        }
+      }
+      if (res2 <= sc.res_thr) break;
+    }
+    for (int l = 0; l < 4; l++) {
+      for (int m = 0; m < 3; m++) lam[row_of(l, m)] = pl[l].lam[m];
+      lamL[l] = pl[l].lam[3];
+    }
+  } else if (mask) {
     PgsLane pl[4];
     for (int l = 0; l < 4; l++) {
       float rows[3][kRows];
@@ -135,17 +197,19 @@ static void emu_substep(Emu* e, const float* tau) {
   {
     float part[4][6];
     for (int l = 0; l < 4; l++) {
-      float lam3[3] = {lam[row_of(l, 0)], lam[row_of(l, 1)], lam[row_of(l, 2)]};
-      impulse_base_part<NJL>(ln[l], lam3, part[l]);
+      float lam4[4] = {lam[row_of(l, 0)], lam[row_of(l, 1)], lam[row_of(l, 2)], lamL[l]};
+      if (lmask) impulse_base_part4<NJL>(ln[l], lr[l], lam4, part[l]);
+      else impulse_base_part<NJL>(ln[l], lam4, part[l]);
     }
     for (int i = 0; i < 6; i++) { float x[4] = {part[0][i], part[1][i], part[2][i], part[3][i]}; dv0[i] = sum4(x); }
   }
   for (int l = 0; l < 4; l++) {
-    float lam3[3] = {lam[row_of(l, 0)], lam[row_of(l, 1)], lam[row_of(l, 2)]};
-    if (mask) impulse_leg<NJL>(ln[l], sc, lam3, dv0);
+    float lam3[4] = {lam[row_of(l, 0)], lam[row_of(l, 1)], lam[row_of(l, 2)], lamL[l]};
+    if (lmask) impulse_leg4<NJL>(ln[l], lr[l], sc, lam3, dv0);
+    else if (mask) impulse_leg<NJL>(ln[l], sc, lam3, dv0);
     e->cforce[l] = ln[l].active ? lam3[0] * sc.inv_dt : -1.0f;
   }
-  if (mask) {
+  if (mask || lmask) {
     float dw[3], dvl[3];
     mat3_mulv(bw.R, dv0, dw);
     mat3_mulv(bw.R, dv0 + 3, dvl);

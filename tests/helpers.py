@@ -108,3 +108,24 @@ def oracle_policy_episodes(policy, cfg, num_envs, seed=0, torch_seed=0, determin
         obs = torch.from_numpy(o)
     assert finished.all()
     return ret, length, last
+
+
+def limit_states(rng, n, nj, airborne=False):
+    """States whose joints sit at / beyond the +-10 rad URDF limits (one violated joint in 1..4 legs, never two
+    in the same leg, shallow and deep violations, moving in and out), on the ground in a bent stance or in
+    free flight: the inputs of the joint-limit parity tests."""
+    s = stance_states(rng, n, nj, z=0.24, noise=0.1)
+    if airborne:
+        s[:, 2] += 0.8
+        s[:, 10:13] = rng.normal(size=(n, 3))
+    njl = nj // 4
+    for i in range(n):
+        legs = rng.choice(4, size=rng.integers(1, 5), replace=False)
+        for l in legs:
+            k = rng.integers(0, njl)
+            j = l * njl + k
+            sign = rng.choice([-1.0, 1.0])
+            depth = rng.choice([0.0, 0.005, 0.03, 0.2]) if rng.random() < 0.8 else 0.05 * rng.random()
+            s[i, 13 + j] = sign * (10.0 + depth)
+            s[i, 13 + nj + j] = rng.normal() * 6.0
+    return s.astype(np.float32).astype(np.float64)

@@ -275,3 +275,45 @@ def test_step_before_reset_is_an_error():
     _, e, _, _ = pair("solo8")
     with pytest.raises(AssertionError):
         e.step(np.zeros(8, np.float32))
+
+
+@pytest.mark.parametrize("airborne", [False, True])
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_joint_limit_substep_1e3(robot, airborne):
+    """Joint-limit rows ([3P] btMultiBodyJointLimitConstraint): one substep from states with joints at or
+    beyond +-10 rad, with and without foot contacts, lane program against the oracle."""
+    from tests.helpers import limit_states
+    rng = np.random.default_rng(41)
+    o, e, _, m = pair(robot)
+    nj = o.nj
+    errs, rows, ncs = [], [], []
+    for s in limit_states(rng, 80, nj, airborne=airborne):
+        tau = rng.uniform(-3, 3, size=nj).astype(np.float32).astype(np.float64)
+        o.set_state(s); e.set_state(s)
+        o.substep(tau); e.substep(tau)
+        so, se = o.get_state(), e.get_state().astype(np.float64)
+        errs.append((np.abs(so - se) / np.maximum(1.0, np.abs(so))).max())
+        rows.append(o.last_limit_rows)
+        ncs.append(o.get_contacts()[:, 1].sum())
+        assert (o.get_contacts()[:, 1] == e.get_contacts()[:, 1]).all()
+    assert np.mean(rows) > 1.5 and (airborne or np.mean(ncs) > 0.8)      # a leg parked at 10 rad points away from the ground
+    assert max(errs) < TOL_CONTACT, (max(errs), np.median(errs))
+
+
+def test_joint_limits_bound_the_joint_range_in_rollouts():
+    """Random-action rollout of the lane program: without the rows a free leg spins to +-20 rad and beyond,
+    with them |q| stays within a step's travel of the 10 rad limit."""
+    rng = np.random.default_rng(42)
+    worst = {}
+    for jl in (0, 1):
+        cfg = make_config("solo12", task="walk", H=1, episode_length=200, joint_limits=jl)
+        m = SoloModel.resolve("solo12")
+        e = EmuEnv(m, params_from_config(cfg, m), seed=3, env_id=1)
+        e.reset()
+        mx = 0.0
+        r2 = np.random.default_rng(7)
+        for t in range(300):
+            obs, r, d, info = e.step(r2.uniform(-1, 1, size=12), auto_reset=True)
+            mx = max(mx, np.abs(np.asarray(obs)[10:22]).max() * 10.0)
+        worst[jl] = mx
+    assert worst[0] > 12.0 and worst[1] < 10.6, worst

@@ -651,3 +651,56 @@ def test_episode_length_one_and_curriculum_hook():
     assert (goals.abs() >= 1.0 - 1e-5).all() and (goals.abs() <= r0 + 1.0 + 1e-5).all()
     assert (goals.abs() > r0).any()                                   # the larger radius is in use
     envs.close()
+
+
+@pytest.mark.parametrize("build", ["latency", "throughput"])
+@pytest.mark.parametrize("airborne", [False, True])
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_joint_limit_substep_1e3(robot, airborne, build, monkeypatch):
+    """Joint-limit rows ([3P] btMultiBodyJointLimitConstraint): one substep from states with joints at or
+    beyond +-10 rad (one to four legs, shallow / deep violations, moving in and out), with and without foot
+    contacts, both builds of the step kernel, against the oracle."""
+    from tests.helpers import limit_states
+    monkeypatch.setenv("SOLO_STEP_VARIANT", build)
+    rng = np.random.default_rng(43)
+    n = 96
+    sim, m, p = make_sim(robot, n)
+    nj = sim.nj
+    s0 = limit_states(rng, n, nj, airborne=airborne)
+    # every other env stays inside the limits: warps mix limit rows with the plain three-row case
+    s0[1::2, 13:13 + nj] = np.clip(s0[1::2, 13:13 + nj], -9.5, 9.5)
+    tau = rng.uniform(-3, 3, size=(n, nj)).astype(np.float32).astype(np.float64)
+    sim.set_state(cuda(s0))
+    sim.substep(cuda(tau))
+    got = sim.get_state().cpu().numpy().astype(np.float64)
+    con = sim.get_contacts().cpu().numpy()
+    o = OracleEnv(m, p)
+    errs, rows = [], 0
+    for i in range(n):
+        o.set_state(s0[i]); o.substep(tau[i])
+        ref = o.get_state()
+        errs.append((np.abs(ref - got[i]) / np.maximum(1.0, np.abs(ref))).max())
+        rows += o.last_limit_rows
+        assert (o.get_contacts()[:, 1] == con[i, :, 1]).all()
+    assert rows > n / 2
+    assert max(errs) < TOL_CONTACT, (max(errs), np.median(errs))
+    sim.close()
+
+
+def test_joint_limits_bound_the_joint_range_at_full_size():
+    """4096 envs under random actions for 120 steps: no joint ends up more than a step's travel beyond
+    +-10 rad, and with joint_limits = 0 the same rollout spins legs well past it."""
+    from solorl_b200.envs import SoloVecEnv
+    worst = {}
+    for jl in (1, 0):
+        cfg = make_config("solo12", task="walk", H=1, episode_length=400, joint_limits=jl)
+        env = SoloVecEnv(cfg, FULL_N, device="cuda:0", seed=5)
+        env.reset()
+        g = torch.Generator(device="cuda").manual_seed(6)
+        mx = torch.zeros((), device="cuda")
+        for t in range(120):
+            env.step(torch.rand(FULL_N, 12, device="cuda", generator=g) * 2 - 1)
+            mx = torch.maximum(mx, env.sim.get_state()[:, 13:25].abs().max())
+        worst[jl] = float(mx)
+        env.close()
+    assert worst[1] < 10.6 and worst[0] > 15.0, worst

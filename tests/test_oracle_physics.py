@@ -3,11 +3,22 @@ Bullet oracle — PyBullet is not installable here, physics parity is unpinned).
 import numpy as np
 import pytest
 
-from tests.helpers import random_states
+from tests.helpers import random_states, stance_states
 from oracle.oracle import OracleEnv, default_params
 from solorl_b200.model import SoloModel
 
 ROBOTS = ("solo8", "solo12")
+
+
+def params_for(robot, **kw):
+    p = default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def model_and_params(robot, **kw):
+    return SoloModel.builtin(robot), params_for(robot, **kw)
 
 
 @pytest.mark.parametrize("robot", ROBOTS)
@@ -131,3 +142,96 @@ def test_max_coordinate_velocity_clamp():
     e.set_state(s)
     e.substep(np.full(e.nj, 3.0))
     assert np.abs(e.get_state()[13 + e.nj:]).max() <= 100.0 + 1e-12   # [3P] m_maxCoordinateVelocity
+
+
+# ---- joint-limit rows ([3P] btMultiBodyJointLimitConstraint, created by PyBullet's URDF importer) ---------------
+def _free_flight_state(nj, q_over, qd_over, joint=4):
+    s = np.zeros(13 + 2 * nj)
+    s[2] = 1.0; s[6] = 1.0
+    s[13:13 + nj] = np.linspace(-0.5, 0.5, nj)
+    s[13 + nj:] = np.linspace(0.3, -0.3, nj)
+    s[13 + joint] = q_over
+    s[13 + nj + joint] = qd_over
+    return s
+
+
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_joint_limit_row_stops_the_joint(robot):
+    m, p = model_and_params(robot)
+    nj = m.nj
+    dt = p.dt
+    o = OracleEnv(m, p)
+    # upper bound, shallow violation: target velocity = erp * |pen| / dt towards the range
+    o.set_state(_free_flight_state(nj, 10.02, 5.0))
+    o.substep(np.zeros(nj))
+    assert o.last_limit_rows == 1
+    qd = o.get_state()[13 + nj + 4]
+    assert abs(qd - (-0.2 * 0.02 / dt)) < 1e-9
+    # lower bound, deep violation (beyond the split-impulse threshold): velocity target only
+    o.set_state(_free_flight_state(nj, -10.3, -5.0))
+    o.substep(np.zeros(nj))
+    assert o.last_limit_rows == 1 and abs(o.get_state()[13 + nj + 4]) < 1e-9
+    # moving back into the range already faster than the target: the row stays slack (unilateral)
+    o.set_state(_free_flight_state(nj, 10.02, -5.0))
+    o.substep(np.zeros(nj))
+    ref = OracleEnv(m, params_for(robot, joint_limits=0))
+    ref.set_state(_free_flight_state(nj, 10.02, -5.0))
+    ref.substep(np.zeros(nj))
+    assert np.abs(o.get_state() - ref.get_state()).max() < 1e-12
+    # inside the range: no row
+    o.set_state(_free_flight_state(nj, 9.99, 5.0))
+    o.substep(np.zeros(nj))
+    assert o.last_limit_rows == 0
+
+
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_joint_limit_impulse_is_a_pure_joint_impulse(robot):
+    """The velocity change a limit row makes is M^-1 J^T lambda with J a unit vector on the joint: M dv is zero
+    on the base and on every other joint (momentum is conserved, the reaction goes where the mass matrix says)."""
+    m, p = model_and_params(robot)
+    nj = m.nj
+    rng = np.random.default_rng(5)
+    for joint in (0, nj // 2, nj - 1):
+        s = random_states(rng, 1, nj)[0]
+        s[13 + joint] = 10.01
+        s[13 + nj + joint] = 8.0
+        a, b = OracleEnv(m, p), OracleEnv(m, params_for(robot, joint_limits=0))
+        a.set_state(s); b.set_state(s)
+        _, M = a.forward_dynamics_crba(np.zeros(nj), want_M=True)
+        a.substep(np.zeros(nj)); b.substep(np.zeros(nj))
+        assert a.last_limit_rows == 1
+        sa, sb = a.get_state(), b.get_state()
+        dw, dvl = sa[10:13] - sb[10:13], sa[7:10] - sb[7:10]
+        # the mass matrix of forward_dynamics_crba is in spatial coordinates about the WORLD origin: v_O = v + p x w
+        dv = np.concatenate([dw, dvl + np.cross(s[:3], dw), sa[13 + nj:] - sb[13 + nj:]])
+        f = M @ dv
+        lam = f[6 + joint]
+        assert lam < 0 and abs(lam) > 1e-4                      # pushes the joint back (upper bound: negative)
+        f[6 + joint] = 0
+        assert np.abs(f).max() < 1e-9 * max(1.0, abs(lam)) + 1e-10
+
+
+def test_kernel_mode_limit_rows_against_bullet_order():
+    """limit_rows_per_leg = 1 (what the kernels solve: one row per leg, the rows of different legs relaxed as one
+    simultaneous group) against limit_rows_per_leg = 0 (Bullet: every violated joint, strictly row by row):
+    identical with a single limit row, equal to solver tolerance with one row in each of two legs (they couple
+    only through the base), and a second violated joint of the same leg is the documented difference."""
+    m, _ = model_and_params("solo12")
+    rng = np.random.default_rng(6)
+    s = stance_states(rng, 1, 12)[0]
+    s[13 + 1] = 10.05; s[13 + 12 + 1] = 3.0          # FL_HFE over the upper bound
+    a = OracleEnv(m, params_for("solo12", limit_rows_per_leg=1))
+    b = OracleEnv(m, params_for("solo12", limit_rows_per_leg=0))
+    a.set_state(s); b.set_state(s)
+    a.substep(np.zeros(12)); b.substep(np.zeros(12))
+    assert a.last_limit_rows == 1 and b.last_limit_rows == 1
+    assert np.abs(a.get_state() - b.get_state()).max() == 0.0
+    s[13 + 8] = -10.02; s[13 + 12 + 8] = -2.0        # HL_KFE under the lower bound (another leg)
+    a.set_state(s); b.set_state(s)
+    a.substep(np.zeros(12)); b.substep(np.zeros(12))
+    assert a.last_limit_rows == 2 and b.last_limit_rows == 2
+    assert np.abs(a.get_state() - b.get_state()).max() < 1e-3
+    s[13 + 2] = 10.5; s[13 + 12 + 2] = 1.0           # a second joint of the FL leg, deeper: replaces FL_HFE
+    a.set_state(s); b.set_state(s)
+    a.substep(np.zeros(12)); b.substep(np.zeros(12))
+    assert a.last_limit_rows == 2 and b.last_limit_rows == 3
