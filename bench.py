@@ -381,8 +381,8 @@ def run_ours(args):
         "bound": "fp32", "kernel": "step_kernel<3>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this workload
-        # (profiles/r1h_step_kernel_ncu_full.txt); only valid for the default 4096-env Solo12 workload
-        "traffic": 1265152 if (n == ENVS_PER_GPU) else None,
+        # (profiles/r1j_step_kernel_ncu_full.txt); only valid for the default 4096-env Solo12 workload
+        "traffic": 1298432 if (n == ENVS_PER_GPU) else None,
         "traffic_unit": "bytes per launch (algorithmic: %d)" % (algorithmic_bytes_per_env_step(nj, D) * n),
         "peak_source": "FP32 FMA microbenchmark measured live in this run (solo_bench_fma_peak)" if rc == 0
         else "fallback 148 SM x 128 lanes x 2 x 1.965 GHz",
