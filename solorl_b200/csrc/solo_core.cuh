@@ -13,7 +13,8 @@
  * solve is done redundantly by the four lanes.  Contacts are solved in Delassus form
  * A = P^T IA0^-1 P + blockdiag(L): each lane keeps the three rows of its own foot in
  * registers and the projected Gauss-Seidel sweep broadcasts one impulse change per row
- * relaxation with a group-masked shuffle (see PgsLane).
+ * relaxation with a shuffle inside the four-lane group (see PgsLane); a leg whose joint is
+ * at a URDF limit carries a fourth row (see LimitRow / PgsLane4).
  *
  * This formulation is deliberately different from the CPU oracle (oracle/solo_oracle.c:
  * link-COM frames, 6x6 transforms, one impulse-response pass per contact row), which is

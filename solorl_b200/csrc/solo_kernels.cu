@@ -3,14 +3,15 @@
  * Solo8/Solo12 env step.
  *
  * step_kernel: ONE launch per env step.  Thread t of a warp = (env t/4, leg t%4): four lanes
- * per environment, eight environments per warp, one warp per block (at 4096 envs that is 512
- * warps for the 592 warp schedulers of a B200, i.e. one warp per scheduler: the step is a pure
- * dependent-latency problem, so the design minimises the per-warp instruction chain rather than
- * occupancy).  All cross-leg traffic — the sum of the four legs' articulated inertias into the
+ * per environment, eight environments per warp, 4 or 8 warps per block (two builds, see the comment
+ * above step_kernel).  At 4096 envs that is 512 warps for the 592 warp schedulers of a B200: the step
+ * is a dependent-latency problem, so the design minimises the per-warp instruction chain rather than
+ * occupancy.  All cross-leg traffic — the sum of the four legs' articulated inertias into the
  * floating base, the exchange of IA0^-1 P blocks for the Delassus rows, and the one-value
  * broadcast per projected-Gauss-Seidel row relaxation — is full-mask register shuffles of a
- * converged warp; there is no block barrier and no shared-memory staging in the step (shared
- * memory only holds the per-leg model constants).
+ * converged warp.  Shared memory holds the per-leg model constants and one staging tile per warp
+ * through which action words arrive and observation rows leave as whole 128-byte lines; the one
+ * block barrier per substep keeps the warps of an SM on the same instruction-cache lines.
  *
  * HBM layout (structure of arrays, fp32):
  *   base  [cap][16]  : pos3 quat4 linvel3 angvel3 goal2 potential1   (4 x float4 per env)
