@@ -44,9 +44,12 @@ def evaluate(policy, config, num_runs=10, num_envs=None, deterministic=False, se
     limit = max_steps or (int(config["episode_length"]) + 1) * quota + 1
     while (count < quota).any() and steps < limit:
         with torch.no_grad():
-            value, feat = policy.base(obs)
-            mean, logstd = policy.pi_dist(feat)
-            action = mean if deterministic else mean + torch.randn(mean.shape, device=device, generator=g) * logstd.exp()
+            if hasattr(policy, "pi_dist"):                     # PPO actor-critic (agents/ppo/policy.py)
+                value, feat = policy.base(obs)
+                mean, logstd = policy.pi_dist(feat)
+                action = mean if deterministic else mean + torch.randn(mean.shape, device=device, generator=g) * logstd.exp()
+            else:                                              # a deterministic actor, e.g. TD3 (agents/td3/models.py)
+                action = policy(obs)
         obs, reward, done, infos = env.step(action)
         steps += 1
         # one small D2H per step (the done vector); records only when something finished

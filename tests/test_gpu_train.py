@@ -183,3 +183,28 @@ def test_graphed_ppo_update_matches_eager():
         assert agents[0]._graph is not None or it == 0
         for p1, p2 in zip(ac1.parameters(), ac2.parameters()):
             assert torch.allclose(p1, p2, atol=2e-6), it
+
+
+def test_td3_and_ppo_evaluation_clis(tmp_path):
+    """testing/test_ppo.py and testing/test_td3.py on freshly written checkpoints (reference layouts)."""
+    import importlib.util
+    import yaml
+    from tests.helpers import ROOT
+    from solorl_b200.agents import td3, train as ppo
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name[:-3], os.path.join(ROOT, "testing", name))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+    cfg = make_config("solo8", "stand", "torque", 1, episode_length=20)
+    cfg_file = tmp_path / "cfg.yaml"
+    cfg_file.write_text(yaml.safe_dump(cfg))
+    pdir, tdir = tmp_path / "ppo", tmp_path / "td3"
+    ppo.train(_args(logdir=str(pdir), num_agents=64, num_env_steps=64 * 16 * 2), cfg)
+    td3.train(td3.default_args(num_agents=32, start_timesteps=32 * 5, num_env_steps=32 * 30, batch_size=64,
+                               save_interval=10, logdir=str(tdir), max_replay_size=2048), cfg)
+    s1 = load("test_ppo.py").main(["--checkpoint-dir", str(pdir), "--config-file", str(cfg_file), "--num-runs", "20"])
+    s2 = load("test_td3.py").main(["--checkpoint-dir", str(tdir), "--config-file", str(cfg_file), "--num-runs", "20"])
+    for s in (s1, s2):
+        assert s["episodes"] == 20 and 1 <= s["mean_length"] <= 20 and np.isfinite(s["mean_return"])
