@@ -99,19 +99,28 @@ class ReplayBuffer:
 
     def sample(self, mini_batch_size, generator=None):
         idx = torch.randint(0, self._size, (mini_batch_size,), device=self.device, generator=generator)
+        return self.gather(idx)
+
+    def gather(self, idx):
         return (self._observations[idx], self._actions[idx], self._rewards[idx], self._next_observations[idx],
                 self._not_terminal[idx])
 
 
 class TD3:
     def __init__(self, obs_dim, action_dim, gamma=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5, policy_freq=2,
-                 device="cuda"):
+                 device="cuda", use_graph=True):
         self.actor = Actor(obs_dim, action_dim).to(device)
         self.actor_target = copy.deepcopy(self.actor)
-        self.actor_optimizer = torch.optim.Adam(self.actor.parameters(), lr=3e-4)
         self.critic = Critic(obs_dim, action_dim).to(device)
         self.critic_target = copy.deepcopy(self.critic)
-        self.critic_optimizer = torch.optim.Adam(self.critic.parameters(), lr=3e-4)
+        cuda = torch.device(device).type == "cuda"
+        kw = dict(fused=True, capturable=True) if cuda else {}
+        self.actor_optimizer = torch.optim.Adam(self.actor.parameters(), lr=3e-4, **kw)
+        self.critic_optimizer = torch.optim.Adam(self.critic.parameters(), lr=3e-4, **kw)
+        # the update is ~150 small launches; on CUDA it is captured once per kind of step (critic only /
+        # critic + delayed actor and targets) and replayed with a fresh index tensor
+        self.use_graph = bool(use_graph and cuda)
+        self._graphs, self._warm, self._idx = {}, {}, None
         self.gamma, self.tau = float(gamma), float(tau)
         self.policy_noise, self.noise_clip, self.policy_freq = float(policy_noise), float(noise_clip), int(policy_freq)
 
@@ -120,7 +129,48 @@ class TD3:
 
     def train(self, replay_buffer, step, batch_size=100):
         """One TD3 update (td3.py:41-91); returns loss TENSORS (no host sync here)."""
-        obs, action, reward, next_obs, not_done = replay_buffer.sample(batch_size)
+        if not self.use_graph:
+            return self._update(replay_buffer.sample(batch_size), step % self.policy_freq == 0)
+        with_actor = (step % self.policy_freq == 0)
+        if self._idx is None or self._idx.numel() != batch_size:
+            self._idx = torch.zeros(batch_size, dtype=torch.long, device=replay_buffer.device)
+            self._out = {k: [torch.zeros((), device=replay_buffer.device), torch.zeros((), device=replay_buffer.device)]
+                         for k in (False, True)}
+            self._graphs, self._warm = {}, {}
+        self._idx.copy_(torch.randint(0, len(replay_buffer), (batch_size,), device=replay_buffer.device))
+
+        def body():
+            q, a = self._update(replay_buffer.gather(self._idx), with_actor)
+            self._out[with_actor][0].copy_(q)
+            if a is not None:
+                self._out[with_actor][1].copy_(a)
+
+        g = self._graphs.get(with_actor)
+        if g is not None:
+            g.replay()
+        elif self._warm.get(with_actor, 0) < 3:             # eager warm-up (real updates) on a side stream
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                body()
+            torch.cuda.current_stream().wait_stream(s)
+            self._warm[with_actor] = self._warm.get(with_actor, 0) + 1
+        else:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    body()
+                self._graphs[with_actor] = g
+                g.replay()
+            except Exception as e:                           # pragma: no cover - capture is best effort
+                print(f"[td3] CUDA graph capture failed ({e}); continuing eagerly", flush=True)
+                self.use_graph = False
+                body()
+        out = self._out[with_actor]
+        return out[0], (out[1] if with_actor else None)
+
+    def _update(self, batch, with_actor):
+        obs, action, reward, next_obs, not_done = batch
         with torch.no_grad():
             noise = (torch.randn_like(action) * self.policy_noise).clamp(-self.noise_clip, self.noise_clip)
             next_action = self.actor_target(next_obs) + noise
@@ -128,13 +178,13 @@ class TD3:
             target_q = reward + not_done * self.gamma * torch.min(tq1, tq2)
         q1, q2 = self.critic(obs, action)
         critic_loss = F.mse_loss(q1, target_q) + F.mse_loss(q2, target_q)
-        self.critic_optimizer.zero_grad()
+        self.critic_optimizer.zero_grad(set_to_none=False)
         critic_loss.backward()
         self.critic_optimizer.step()
         actor_loss = None
-        if step % self.policy_freq == 0:
+        if with_actor:
             actor_loss = -self.critic.Q1(obs, self.actor(obs)).mean()
-            self.actor_optimizer.zero_grad()
+            self.actor_optimizer.zero_grad(set_to_none=False)
             actor_loss.backward()
             self.actor_optimizer.step()
             with torch.no_grad():

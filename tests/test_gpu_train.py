@@ -208,3 +208,28 @@ def test_td3_and_ppo_evaluation_clis(tmp_path):
     s2 = load("test_td3.py").main(["--checkpoint-dir", str(tdir), "--config-file", str(cfg_file), "--num-runs", "20"])
     for s in (s1, s2):
         assert s["episodes"] == 20 and 1 <= s["mean_length"] <= 20 and np.isfinite(s["mean_return"])
+
+
+def test_graphed_td3_update_matches_eager():
+    import copy
+    from solorl_b200.agents.td3 import TD3, ReplayBuffer
+    torch.manual_seed(0)
+    a = TD3(12, 4, device="cuda", use_graph=True)
+    b = TD3(12, 4, device="cuda", use_graph=False)
+    for src, dst in ((a.actor, b.actor), (a.critic, b.critic), (a.actor_target, b.actor_target),
+                     (a.critic_target, b.critic_target)):
+        dst.load_state_dict(copy.deepcopy(src.state_dict()))
+    rb = ReplayBuffer(4096, 12, 4, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    rb.append_batch(torch.randn(3000, 12, device="cuda", generator=g), torch.randn(3000, 4, device="cuda", generator=g).tanh(),
+                    torch.randn(3000, device="cuda", generator=g), torch.randn(3000, 12, device="cuda", generator=g),
+                    (torch.rand(3000, device="cuda", generator=g) > 0.1).float())
+    for step in range(12):                      # 3 eager warm-ups per kind of step, then capture, then replays
+        for agent in (a, b):
+            torch.manual_seed(50 + step)        # same batch indices and the same target-smoothing noise
+            q, al = agent.train(rb, step, 256)
+            assert torch.isfinite(q)
+    assert a._graphs.get(True) is not None and a._graphs.get(False) is not None
+    for m1, m2 in ((a.actor, b.actor), (a.critic, b.critic), (a.actor_target, b.actor_target)):
+        for p1, p2 in zip(m1.parameters(), m2.parameters()):
+            assert torch.allclose(p1, p2, atol=5e-6)
