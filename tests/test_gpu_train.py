@@ -233,3 +233,27 @@ def test_graphed_td3_update_matches_eager():
     for m1, m2 in ((a.actor, b.actor), (a.critic, b.critic), (a.actor_target, b.actor_target)):
         for p1, p2 in zip(m1.parameters(), m2.parameters()):
             assert torch.allclose(p1, p2, atol=5e-6)
+
+
+def test_reference_shaped_cli_invocation_configs0(tmp_path):
+    """BASELINE configs[0]: `train_ppo.py --config-file configs/basic.yaml --num-agents 64` exactly as the
+    reference README runs it (rollout length = episode_length = 400, README.md:34-36 hyper-parameters), for two
+    updates; then the checkpoint is rolled out with testing/test_ppo.py."""
+    import importlib.util
+    from tests.helpers import ROOT
+
+    def load(rel):
+        spec = importlib.util.spec_from_file_location(os.path.basename(rel)[:-3], os.path.join(ROOT, rel))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+    out = load("training/train_ppo.py").main([
+        "--config-file", os.path.join(ROOT, "configs", "basic.yaml"), "--num-agents", "64", "--lr", "2.5e-4",
+        "--clip-param", "0.1", "--ppo-epoch", "5", "--mini-batch-size", "512", "--use-gae", "--use-linear-lr-decay",
+        "--num-env-steps", str(64 * 400 * 2), "--log-interval", "1", "--logdir", str(tmp_path), "--timestamp", "t"])
+    assert out["updates"] == 2 and out["last"]["episodes"] > 0
+    run = [d for d in os.listdir(tmp_path) if d.startswith("SoloBase_")]
+    assert len(run) == 1 and os.path.exists(os.path.join(tmp_path, run[0], "solo.pt"))
+    s = load("testing/test_ppo.py").main(["--checkpoint-dir", os.path.join(tmp_path, run[0]), "--config-file",
+                                          os.path.join(ROOT, "configs", "basic.yaml"), "--num-runs", "10"])
+    assert s["episodes"] == 10
