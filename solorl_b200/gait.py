@@ -190,7 +190,7 @@ class SoloGaitVecEnv:
 
     OBS_DIM = 64          # soloGaitEnvContact.py:36-38
 
-    def __init__(self, config, num_envs, device=None, seed=0, controller_factory=None):
+    def __init__(self, config, num_envs, device=None, seed=0, controller_factory=None, cuda_graph=True):
         self.config = dict(config)
         self.dt = float(config.get("dt", 0.002))                       # baseControlEnv.py:37
         self.T_gait = float(config.get("T_gait", 0.32))
@@ -228,6 +228,8 @@ class SoloGaitVecEnv:
         self.dr = torch.zeros(self.nenvs, 3, **f)                      # Torque_pen, body_velocity, Energy_pen
         self.last_info = None
         self._was_reset = False
+        self.cuda_graph = bool(cuda_graph)
+        self._graph = None
 
     # ---- helpers ---------------------------------------------------------------------------
     def _new_random_vel(self, n):
@@ -269,7 +271,7 @@ class SoloGaitVecEnv:
         if self.auto_vel_switch:
             self.vel_ref = torch.where(sel.unsqueeze(1), self._new_random_vel(self.nenvs), self.vel_ref)
         self.past_gaits = torch.where(sel.unsqueeze(1), torch.full_like(self.past_gaits, 9), self.past_gaits)
-        self.timestep = torch.where(sel, torch.zeros_like(self.timestep), self.timestep)
+        self.timestep.masked_fill_(sel, 0)
         self.ep_reward = torch.where(sel, torch.zeros_like(self.ep_reward), self.ep_reward)
         self.ep_length = torch.where(sel, torch.zeros_like(self.ep_length), self.ep_length)
         self.dr = torch.where(sel.unsqueeze(1), torch.zeros_like(self.dr), self.dr)
@@ -280,28 +282,8 @@ class SoloGaitVecEnv:
         assert self._was_reset, "env.reset() must be called before step"          # baseControlEnv.py:135
         a = torch.as_tensor(action, device=self.device).long().reshape(self.nenvs)
         self.past_gaits = torch.cat([self.past_gaits[:, 1:], a.unsqueeze(1)], dim=1)   # soloGaitEnvContact.py:42
-        self.timestep = self.timestep + 1
-        r = self.robot
-        r.UpdateMeasurment()
-        alive = ~self._terminated()[0]
-        torque_pen = torch.zeros(self.nenvs, device=self.device)
-        vel_pen = torch.zeros_like(torque_pen)
-        joints_power = torch.zeros(self.nenvs, 12, device=self.device)
-        for _ in range(self.k_rl):                                                 # baseControlEnv.py:147-162
-            r.UpdateMeasurment()
-            P, D, q_des, v_des, tau_ff = self.controller.compute(r, a, self.vel_ref)
-            r.SetDesiredJointPDgains(P, D)
-            r.SetDesiredJointPosition(q_des)
-            r.SetDesiredJointVelocity(v_des)
-            r.SetDesiredJointTorque(tau_ff)
-            r.SendCommand(WaitEndOfCycle=False)
-            live = alive.float()
-            torque_pen = torque_pen + live * (r.tau_ff ** 2).sum(1)
-            vel_pen = vel_pen + live * ((self.vel_ref - self.get_base_vel()) ** 2).sum(1)
-            joints_power = joints_power + live.unsqueeze(1) * self.get_joints_power()
-            # `if done: break`: an env that terminates mid-step stops accumulating
-            z = r.sim.get_state()[:, 2]
-            alive = alive & ~(z < 0.11)
+        self.timestep += 1                       # in place: the captured tick loop reads this tensor
+        torque_pen, vel_pen, joints_power = self._run_ticks(a)
         if self.auto_vel_switch:                                                   # switch_velocities :302-312
             sw = (self.timestep % self.vel_switch) == 0
             self.vel_ref = torch.where(sw.unsqueeze(1), self._new_random_vel(self.nenvs), self.vel_ref)
@@ -324,6 +306,64 @@ class SoloGaitVecEnv:
         if bool(done.any()):                                                       # worker auto-reset (envs.py:38-40)
             obs = torch.where(done.unsqueeze(1), self.reset(donef), obs)
         return obs, reward, donef, GaitInfos(self.last_info, donef)
+
+    # ---- the k_rl controller ticks of one RL step (baseControlEnv.py:147-162) -----------------------------
+    def _ticks(self, a):
+        r = self.robot
+        r.UpdateMeasurment()
+        alive = ~self._terminated()[0]
+        torque_pen = torch.zeros(self.nenvs, device=self.device)
+        vel_pen = torch.zeros_like(torque_pen)
+        joints_power = torch.zeros(self.nenvs, 12, device=self.device)
+        for _ in range(self.k_rl):
+            r.UpdateMeasurment()
+            P, D, q_des, v_des, tau_ff = self.controller.compute(r, a, self.vel_ref)
+            r.SetDesiredJointPDgains(P, D)
+            r.SetDesiredJointPosition(q_des)
+            r.SetDesiredJointVelocity(v_des)
+            r.SetDesiredJointTorque(tau_ff)
+            r.SendCommand(WaitEndOfCycle=False)
+            live = alive.float()
+            torque_pen = torque_pen + live * (r.tau_ff ** 2).sum(1)
+            vel_pen = vel_pen + live * ((self.vel_ref - self.get_base_vel()) ** 2).sum(1)
+            joints_power = joints_power + live.unsqueeze(1) * self.get_joints_power()
+            # `if done: break`: an env that terminates mid-step stops accumulating
+            z = r.sim.get_state()[:, 2]
+            alive = alive & ~(z < 0.11)
+        return torque_pen, vel_pen, joints_power
+
+    def _run_ticks(self, a):
+        """Eagerly, or — the ~60 small launches per tick x 80 ticks cost far more CPU time than GPU time — as ONE
+        CUDA graph captured on first use (the controller must then be capturable: tensor ops only, no host
+        reads; pass cuda_graph=False otherwise)."""
+        if not self.cuda_graph:
+            return self._ticks(a)
+        if self._graph is None:
+            try:
+                self._g_a = torch.zeros(self.nenvs, dtype=torch.long, device=self.device)
+                self._g_vel = torch.zeros(self.nenvs, 6, device=self.device)
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                state = self.robot.sim.get_state().clone()
+                with torch.cuda.stream(s):                    # warm-up on a side stream, then restore the state
+                    self._ticks(a)
+                torch.cuda.current_stream().wait_stream(s)
+                self.robot.sim.set_state(state)
+                real_vel = self.vel_ref
+                self.vel_ref = self._g_vel                    # the captured program reads the static copies
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._g_out = self._ticks(self._g_a)
+                self.vel_ref = real_vel
+                self._graph = g
+            except Exception as e:                            # pragma: no cover - capture is best effort
+                print(f"[gait] CUDA graph capture of the tick loop failed ({e}); running it eagerly", flush=True)
+                self.cuda_graph = False
+                return self._ticks(a)
+        self._g_a.copy_(a)
+        self._g_vel.copy_(self.vel_ref)
+        self._graph.replay()
+        return tuple(t.clone() for t in self._g_out)
 
     def increment_curriculum(self, val=0.1):                                       # :314-323
         if self.use_curriculum:

@@ -130,3 +130,22 @@ def test_make_vec_envs_accepts_the_contact_env():
     obs, rew, done, infos = envs.step(torch.tensor([1, 2, 3, 4]))
     assert obs.shape == (4, 64) and rew.shape == (4, 1) and done.shape == (4,)
     envs.close()
+
+
+def test_graphed_tick_loop_matches_eager():
+    """The 80-tick controller loop of one RL step replayed as one CUDA graph against the eager loop: same
+    observations, rewards and done flags over several RL steps including an auto-reset."""
+    from solorl_b200.gait import SoloGaitVecEnv
+    cfg = {"solo12": True, "episode_length": 3, "mode": "headless", "flat_ground": True, "auto_vel_switch": True}
+    envs = [SoloGaitVecEnv(cfg, 64, seed=3, cuda_graph=g) for g in (True, False)]
+    o1, o2 = envs[0].reset(), envs[1].reset()
+    assert torch.equal(o1, o2)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(5):
+        a = torch.randint(0, 9, (64,), device="cuda", generator=gen)
+        r1, r2 = envs[0].step(a), envs[1].step(a)
+        assert torch.allclose(r1[0], r2[0], atol=1e-6) and torch.allclose(r1[1], r2[1], atol=1e-6)
+        assert torch.equal(r1[2], r2[2])
+    assert envs[0]._graph is not None
+    for e in envs:
+        e.close()
