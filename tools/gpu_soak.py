@@ -1,0 +1,27 @@
+"""Soak: long random-action rollouts, counting non-finite-state guard hits and checking ranges (GPU box)."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from solorl_b200.envs import SoloVecEnv
+
+for robot, task, control in (("solo12", "walk", "torque"), ("solo8", "stand", "pd"), ("solo12", "pointgoal", "vpd")):
+    cfg = {"model_urdf": robot, "mode": "headless", "episode_length": 400, "frame_skip": 4, "control": control,
+           "task": task, "num_history_stack": 1, "gains": [5., .2]}
+    n = 4096
+    env = SoloVecEnv(cfg, n, device="cuda:0", seed=11)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    nan = 0; eps = 0; mxq = 0.0; mxv = 0.0; lens = []
+    for t in range(1500):
+        a = torch.randn(n, env.sim.act_dim, device="cuda", generator=g) * (3.0 if t % 7 == 0 else 1.0)
+        obs, rew, done, infos = env.step(a)
+        if t % 25 == 0:
+            assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+            s = env.sim.get_state()
+            nj = env.sim.nj
+            mxq = max(mxq, float(s[:, 13:13 + nj].abs().max())); mxv = max(mxv, float(s[:, 13 + nj:].abs().max()))
+            r = infos.done_records()
+            nan += int(r["nan"].sum()); eps += len(r); lens += r["episode_length"].tolist()
+    print(f"{robot}/{task}/{control}: sampled {eps} finished episodes, nan-guard hits {nan}, mean length {np.mean(lens):.1f}, "
+          f"max |q| {mxq:.2f} rad, max |qd| {mxv:.1f} rad/s", flush=True)
+    env.close()
