@@ -418,6 +418,11 @@ def run_ours(args):
         saturated.update({"achieved_tflops": ach, "peak_tflops": peak, "frac": ach / peak})
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        try:                                    # the reference itself, if it ever becomes runnable here
+            import pybullet  # noqa: F401
+            line["pybullet_direct"] = "installed but not wired: see BASELINE.md B0"
+        except Exception:
+            line["pybullet_direct"], line["reason"] = None, "pybullet not installed"
     print(json.dumps(line), flush=True)
     env.close()
 
