@@ -320,14 +320,14 @@ def run_ours(args):
     h_obs = torch.empty(n, D, dtype=torch.float32).pin_memory()
     h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
     h_done = torch.empty(n, dtype=torch.float32).pin_memory()
-    np_act = [t.numpy() for t in h_act]
-    np_obs, np_rew, np_done = h_obs.numpy(), h_rew.numpy(), h_done.numpy()
+    p_act = [t.data_ptr() for t in h_act]                 # pinned host addresses, reused every step
+    p_obs, p_rew, p_done = h_obs.data_ptr(), h_rew.data_ptr(), h_done.data_ptr()
     for i in range(3):
-        sim.step_host(np_act[i % 4], np_obs, np_rew, np_done)
+        sim.step_host_ptr(p_act[i % 4], p_obs, p_rew, p_done)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        sim.step_host(np_act[i % 4], np_obs, np_rew, np_done)
+        sim.step_host_ptr(p_act[i % 4], p_obs, p_rew, p_done)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:

@@ -80,6 +80,11 @@ class SoloSim:
                                          C.c_void_p(reward_np.ctypes.data), C.c_void_p(done_np.ctypes.data),
                                          self._stream()), self.h)
 
+    def step_host_ptr(self, actions_ptr, obs_ptr, reward_ptr, done_ptr):
+        """The same call with raw host addresses (ints), for callers that reuse their buffers: building four
+        ctypes pointers from numpy arrays costs more than the C call itself."""
+        _lib.check(self.L.solo_step_host(self.h, actions_ptr, obs_ptr, reward_ptr, done_ptr, self._stream()), self.h)
+
     def get_observation(self):
         out = torch.empty(self.n, self.d, dtype=torch.float32, device=self.device)
         _lib.check(self.L.solo_get_observation(self.h, _ptr(out), self._stream()), self.h)
