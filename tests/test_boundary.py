@@ -96,9 +96,11 @@ def test_create_rejects_bad_arguments():
 
 
 def test_product_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "solorl_b200")
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/: the package, the CLIs and
+    the developer tools outside tests/ must not."""
     bad = []
-    for dp, _, files in os.walk(pkg):
+    walks = [os.walk(os.path.join(ROOT, d)) for d in ("solorl_b200", "tools", "training", "testing")]
+    for dp, _, files in (x for w in walks for x in w):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dp, f), errors="ignore").read()

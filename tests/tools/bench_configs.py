@@ -1,5 +1,5 @@
 """The configs of BASELINE.json / BASELINE.md §3 side by side: GPU env-steps/s (device resident, back to back) next
-to the CPU restatement on all host threads and on one.  Run on a GPU box: python tools/bench_configs.py"""
+to the CPU restatement on all host threads and on one.  Run on a GPU box: python tests/tools/bench_configs.py"""
 import os
 import sys
 import time
@@ -7,7 +7,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.oracle import OracleVecEnv, lib  # noqa: E402  (CPU baseline leg)
 from solorl_b200.abi import params_from_config  # noqa: E402
 from solorl_b200.envs import SoloVecEnv  # noqa: E402

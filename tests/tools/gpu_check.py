@@ -1,5 +1,5 @@
 """Quick GPU sanity run: parity of the CUDA path against the CPU oracle and a rough timing.
-Usage (on a GPU box): python tools/gpu_check.py"""
+Usage (on a GPU box): python tests/tools/gpu_check.py"""
 import os
 import sys
 import time
@@ -7,7 +7,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.oracle import OracleEnv, default_params  # noqa: E402
 from solorl_b200.abi import params_from_config  # noqa: E402
 from solorl_b200.envs import SoloVecEnv  # noqa: E402

@@ -1,7 +1,7 @@
 """Find the worst single-substep sample against the oracle and print its anatomy."""
 import os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from tests.helpers import make_config, stance_states
 from solorl_b200.abi import params_from_config
 from solorl_b200.model import SoloModel
