@@ -116,6 +116,15 @@ def dist_setup(n_gpus):
     return rank, world, local
 
 
+def host_threads():
+    """All host threads this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to
+    every rank, which would time the CPU arm on a single thread at N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(seconds=12.0, nthreads=None):
     """The oracle port on all host threads over a bounded sample of the same workload."""
     from oracle.oracle import OracleVecEnv, lib
@@ -123,7 +132,7 @@ def cpu_baseline(seconds=12.0, nthreads=None):
     from solorl_b200.model import SoloModel
     m = SoloModel.resolve(CONFIG["model_urdf"])
     p = params_from_config(CONFIG, m)
-    nthreads = nthreads or lib().oracle_max_threads()
+    nthreads = nthreads or host_threads()
     n = 32 * nthreads
     v = OracleVecEnv(m, p, n, seed=1, nthreads=nthreads)
     v.reset()
@@ -151,7 +160,7 @@ def run_reference(args):
     from solorl_b200.model import SoloModel
     m = SoloModel.resolve(CONFIG["model_urdf"])
     p = params_from_config(CONFIG, m)
-    nthreads = lib().oracle_max_threads()
+    nthreads = host_threads()
     n = 32 * nthreads
     v = OracleVecEnv(m, p, n, seed=1, nthreads=nthreads)
     v.reset()

@@ -83,7 +83,7 @@ def test_ppo_update_keeps_ranks_in_lockstep(tmp_path):
 
 def test_reference_arm_under_torchrun_prints_one_line():
     """bench.py --impl reference at N=2: rank 0 alone runs and prints, the other rank exits 0."""
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env = dict(os.environ)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(30300 + os.getpid() % 400),
            os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"]
@@ -94,3 +94,5 @@ def test_reference_arm_under_torchrun_prints_one_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must still use all host threads
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))

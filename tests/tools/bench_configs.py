@@ -55,7 +55,7 @@ def main():
             ("2 Solo12 walk (bench.py)", dict(base, model_urdf="solo12", task="walk", control="torque", num_history_stack=1), 4096),
             ("2b Solo12 pointgoal (basic12.yaml)", dict(base, model_urdf="solo12", task="pointgoal", control="torque", num_history_stack=1), 4096),
             ("3 basic_pd.yaml", dict(base, model_urdf="solo8", task="stand", control="pd", gains=[5., .2], num_history_stack=0), 16384)]
-    nthr = lib().oracle_max_threads()
+    nthr = len(os.sched_getaffinity(0))
     print(f"# {torch.cuda.get_device_name(0)}; CPU restatement (fp64 oracle, not PyBullet) on {nthr} host threads and on 1")
     print(f"# {'config':38s} {'envs':>6s} {'GPU env-steps/s':>16s} {'CPU all threads':>16s} {'CPU 1 thread':>13s} {'GPU/CPU-all':>11s}")
     for name, cfg, n in rows:
