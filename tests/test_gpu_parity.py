@@ -704,3 +704,43 @@ def test_joint_limits_bound_the_joint_range_at_full_size():
         worst[jl] = float(mx)
         env.close()
     assert worst[1] < 10.6 and worst[0] > 15.0, worst
+
+
+@pytest.mark.parametrize("build", ["latency", "throughput"])
+@pytest.mark.parametrize("n", [1, 37, 264])
+def test_outputs_stay_inside_their_buffers(n, build, monkeypatch):
+    """Canaries around every caller-owned output of solo_step / solo_reset / solo_get_* (ragged batches, both
+    builds, the staged whole-line observation stores): nothing outside [0, n) rows is written."""
+    import ctypes as C
+    from solorl_b200 import _lib
+    monkeypatch.setenv("SOLO_STEP_VARIANT", build)
+    sim, m, p = make_sim("solo12", n, task="pointgoal", H=2, episode_length=4)
+    L, h = sim.L, sim.h
+    pad, canary = 512, -12345.5
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def guarded(count):
+        buf = torch.full((count + 2 * pad,), canary, dtype=torch.float32, device="cuda")
+        return buf, C.c_void_p(buf[pad:].data_ptr())
+
+    def intact(buf, count):
+        return bool((buf[:pad] == canary).all()) and bool((buf[pad + count:] == canary).all())
+
+    obs, p_obs = guarded(n * sim.d)
+    rew, p_rew = guarded(n)
+    done, p_done = guarded(n)
+    _lib.check(L.solo_reset(h, None, p_obs, stream), h)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(7):                                   # includes auto-resets (episode_length 4)
+        a = (torch.rand(n, 12, device="cuda", generator=g) * 2 - 1).contiguous()
+        _lib.check(L.solo_step(h, C.c_void_p(a.data_ptr()), p_obs, p_rew, p_done, stream), h)
+    torch.cuda.synchronize()
+    assert intact(obs, n * sim.d) and intact(rew, n) and intact(done, n)
+    assert torch.isfinite(obs[pad:pad + n * sim.d]).all() and (obs[pad:pad + n * sim.d] != canary).any()
+    for fn, count in ((L.solo_get_observation, n * sim.d), (L.solo_get_state, n * (13 + 24)),
+                      (L.solo_get_contacts, n * 12), (L.solo_get_feet, n * 12)):
+        buf, ptr = guarded(count)
+        _lib.check(fn(h, ptr, stream), h)
+        torch.cuda.synchronize()
+        assert intact(buf, count) and (buf[pad:pad + count] != canary).all()
+    sim.close()
