@@ -219,6 +219,12 @@ int solo_set_goals(SoloHandle* h, const float* d_goals, void* stream);
  * solo.py:310-323), has_point, normal force [N]. d_out float[N, 4, 3]. */
 int solo_get_contacts(SoloHandle* h, float* d_out, void* stream);
 
+/* Parity hook: overwrite the contact record that solo_get_contacts / the observation's contact flags read
+ * (what p.getContactPoints would return at solo.py:313-317): d_force float[N, 4] = normal force per foot,
+ * a negative value = no contact point.  Lets the 1e-6 observation test inject contact sets on both sides of
+ * the 0.2 N flag threshold (solo.py:310-323); solo_set_state clears the record again. */
+int solo_set_contacts(SoloHandle* h, const float* d_force, void* stream);
+
 /* Measurement hook: work done by the last env step, per env: d_out int32[N,2] =
  * (sum over substeps of feet in contact, sum over substeps of feet-in-contact x PGS sweeps run).
  * bench.py turns these into the algorithmic FLOPs of the launch. */
@@ -262,7 +268,8 @@ int solo_episode_stats(SoloHandle* h, SoloEpisodeStats* d_stats, void* stream);
  * The caller initialises d_acc (zeros; +inf / -inf / 0 for [10..12]). */
 int solo_accumulate_episode_stats(SoloHandle* h, const float* d_done, double* d_acc, void* stream);
 
-/* Curriculum hook (increment_goal_radius, solo.py:332-334). */
+/* Curriculum hook (increment_goal_radius, solo.py:332-334).  The radius is kept in device memory, so steps
+ * already captured into a CUDA graph see the new value; the call waits for the device to drain first. */
 int solo_set_goal_radius(SoloHandle* h, double goal_radius);
 
 /* Reverse-scan GAE over a device-resident rollout, replaces

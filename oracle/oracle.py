@@ -76,6 +76,10 @@ def lib():
         L.oracle_forward_dynamics_crba.argtypes = [vp, dp, dp, dp]
         L.oracle_substep.argtypes = [vp, dp]
         L.oracle_get_contacts.argtypes = [vp, dp]
+        L.oracle_set_contacts.argtypes = [vp, dp]
+        ip = C.POINTER(C.c_int)
+        L.oracle_contact_rows.argtypes = [vp, dp, dp, dp, dp, ip, ip, dp]
+        L.oracle_contact_rows.restype = C.c_int
         L.oracle_energy.argtypes = [vp]
         L.oracle_energy.restype = C.c_double
         L.oracle_foot_positions.argtypes = [vp, dp]
@@ -211,6 +215,24 @@ class OracleEnv:
         out = np.zeros((4, 3))
         self.L.oracle_get_contacts(self.h, _dp(out))
         return out
+
+    def set_contacts(self, force):
+        f = np.ascontiguousarray(force, dtype=np.float64)
+        assert f.shape == (4,)
+        self.L.oracle_set_contacts(self.h, _dp(f))
+
+    def contact_rows(self, tau):
+        """Constraint rows the next substep(tau) would build (env not advanced): dict with J, U [rows, 6+nj],
+        target, kind (0 normal, 1/2 friction, 3 joint limit), owner, vstar."""
+        tau = np.ascontiguousarray(tau, dtype=np.float64)
+        nd, cap = 6 + self.nj, 12 + 2 * self.nj
+        J, U = np.zeros((cap, nd)), np.zeros((cap, nd))
+        target, vstar = np.zeros(cap), np.zeros(nd)
+        kind, owner = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        ip = C.POINTER(C.c_int)
+        n = self.L.oracle_contact_rows(self.h, _dp(tau), _dp(J), _dp(U), _dp(target), kind.ctypes.data_as(ip),
+                                       owner.ctypes.data_as(ip), _dp(vstar))
+        return dict(J=J[:n], U=U[:n], target=target[:n], kind=kind[:n], owner=owner[:n], vstar=vstar)
 
     def energy(self):
         return self.L.oracle_energy(self.h)

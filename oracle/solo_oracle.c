@@ -799,6 +799,98 @@ void oracle_substep(OracleEnv* e, const double* tau) {
   for (int i = 0; i < m->num_links; i++) e->q[i] += dt * e->qd[i];
 }
 
+/* Independent check hook for the contact pipeline (tests/test_oracle_physics.py): the constraint rows the
+ * next oracle_substep(tau) would build, WITHOUT advancing the env.  Row order = the sweep order (limit rows,
+ * contact normals, then the friction pair of each contact).  Per row r: J[r][nd] (Jacobian), U[r][nd]
+ * (M^-1 J^T by the ABA impulse-response pass), target[r] = positional + velocity error (rhs before the
+ * 1/diag scaling), kind[r] = 0 normal / 1,2 friction / 3 joint limit, owner[r] = contact index (limit rows:
+ * the link).  vstar[nd] = the unconstrained velocity v + dt*qdd (clamped).  Returns the number of rows.
+ * The test recomputes J M^-1 J^T from the dense CRBA mass matrix and solves the same LCP with 10^4 sweeps. */
+int oracle_contact_rows(const OracleEnv* e0, const double* tau, double* J, double* U, double* target,
+                        int* kind, int* owner, double* vstar) {
+  OracleEnv ecopy = *e0;
+  OracleEnv* e = &ecopy;
+  const SoloModelTable* m = &e->m;
+  const SoloSimParams* p = &e->p;
+  AbaWork W;
+  int nd = 6 + e->nj, nr = 0;
+  double qdd[MAXD], dt = p->dt;
+  aba_forward(e, &W, tau, qdd);
+  int nc = 0, cfoot[SOLO_MAX_FEET];
+  v3 cpt[SOLO_MAX_FEET];
+  double cdist[SOLO_MAX_FEET];
+  const v3 nrm = {0, 0, 1};
+  for (int f = 0; f < m->num_feet; f++) {
+    int l = m->foot_link[f];
+    v3 off, c;
+    for (int k = 0; k < 3; k++) off[k] = m->foot_center[f][k] - m->com[l][k];
+    m3mulv(c, W.Rw[l], off);
+    for (int k = 0; k < 3; k++) c[k] += W.pw[l][k];
+    double dist = c[2] - m->foot_radius;
+    if (dist < p->contact_margin) {
+      cfoot[nc] = f; cdist[nc] = dist;
+      v3set(cpt[nc], c[0], c[1], c[2] - m->foot_radius);
+      nc++;
+    }
+  }
+  for (int k = 0; k < 3; k++) { e->vang[k] += dt * qdd[k]; e->vlin[k] += dt * qdd[3 + k]; }
+  for (int j = 0; j < e->nj; j++) e->qd[e->link_of_dof[j]] += dt * qdd[6 + j];
+  clamp_velocities(e);
+  double vel[MAXD];
+  for (int k = 0; k < 3; k++) { vel[k] = e->vang[k]; vel[3 + k] = e->vlin[k]; }
+  for (int j = 0; j < e->nj; j++) vel[6 + j] = e->qd[e->link_of_dof[j]];
+  for (int k = 0; k < nd; k++) vstar[k] = vel[k];
+  if (p->joint_limits) {
+    const double lim = p->joint_state_limit;
+    for (int i = 0; i < m->num_links; i++) {
+      if (m->jtype[i] != SOLO_JOINT_REVOLUTE) continue;
+      for (int side = 0; side < 2; side++) {
+        const double pen = side == 0 ? e0->q[i] + lim : lim - e0->q[i];
+        const double dir = side == 0 ? 1.0 : -1.0;
+        if (pen > 0) continue;
+        double* Jr = J + (size_t)nr * nd; double* Ur = U + (size_t)nr * nd;
+        const v3 zero = {0, 0, 0};
+        for (int k = 0; k < nd; k++) Jr[k] = 0;
+        Jr[6 + e->dof_of_link[i]] = dir;
+        impulse_response(e, &W, -1, zero, zero, i, dir, Ur);
+        const double positional = (pen > p->split_impulse_threshold) ? -pen * p->joint_limit_erp / dt : 0.0;
+        target[nr] = positional - rowdot(nd, Jr, vel);
+        kind[nr] = 3; owner[nr] = i; nr++;
+      }
+    }
+  }
+  v3 t1, t2;
+  plane_space(nrm, t1, t2);
+  const double* dirs[3] = {nrm, t1, t2};
+  for (int pass = 0; pass < 2; pass++) {          /* normals of every contact first, then the friction pairs */
+    for (int c = 0; c < nc; c++) {
+      int l = m->foot_link[cfoot[c]];
+      for (int r = (pass == 0 ? 0 : 1); r < (pass == 0 ? 1 : 3); r++) {
+        double* Jr = J + (size_t)nr * nd; double* Ur = U + (size_t)nr * nd;
+        contact_jacobian(e, &W, l, cpt[c], dirs[r], Jr);
+        impulse_response(e, &W, l, cpt[c], dirs[r], -1, 0.0, Ur);
+        double verr = -rowdot(nd, Jr, vel), perr = 0;
+        if (r == 0) {
+          double pen = cdist[c] + p->contact_slop;
+          if (pen > 0) verr -= pen / dt; else perr = -pen * p->contact_erp / dt;
+        }
+        target[nr] = perr + verr;
+        kind[nr] = r; owner[nr] = c; nr++;
+      }
+    }
+  }
+  return nr;
+}
+
+/* parity hook: overwrite the contact record (what p.getContactPoints returned, solo.py:313-317):
+ * force[f] < 0 = no contact point on foot f */
+void oracle_set_contacts(OracleEnv* e, const double* force) {
+  for (int f = 0; f < e->m.num_feet; f++) {
+    e->c_has[f] = force[f] >= 0;
+    e->c_force[f] = force[f] >= 0 ? force[f] : 0.0;
+  }
+}
+
 void oracle_forward_dynamics(OracleEnv* e, const double* tau, double* qdd) {
   AbaWork W;
   aba_forward(e, &W, tau, qdd);

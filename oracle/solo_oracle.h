@@ -81,6 +81,10 @@ void oracle_forward_dynamics_crba(OracleEnv* e, const double* tau, double* qdd, 
 void oracle_substep(OracleEnv* e, const double* tau);
 /* contact record of the last substep: out[4][3] = flag, has_point, normal force */
 void oracle_get_contacts(const OracleEnv* e, double* out);
+void oracle_set_contacts(OracleEnv* e, const double* force4);
+/* constraint rows of the next substep without advancing the env (see solo_oracle.c); J, U: [rows][6+nj] */
+int oracle_contact_rows(const OracleEnv* e, const double* tau, double* J, double* U, double* target,
+                        int* kind, int* owner, double* vstar);
 /* total mechanical energy (kinetic + potential) of the current state */
 double oracle_energy(OracleEnv* e);
 /* world position of foot sphere centres: out[4][3] */

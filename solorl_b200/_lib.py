@@ -22,7 +22,7 @@ SYMBOLS = [
     "solo_set_state", "solo_set_goals", "solo_get_contacts", "solo_get_work_counters", "solo_forward_dynamics",
     "solo_substep", "solo_action_to_torque", "solo_episode_stats", "solo_set_goal_radius",
     "solo_gae", "solo_launch_count", "solo_actuator_step", "solo_get_feet",
-    "solo_accumulate_episode_stats",
+    "solo_accumulate_episode_stats", "solo_set_contacts",
 ]
 
 
@@ -58,6 +58,7 @@ def lib():
     L.solo_set_state.argtypes = [vp, fp, vp]
     L.solo_set_goals.argtypes = [vp, fp, vp]
     L.solo_get_contacts.argtypes = [vp, fp, vp]
+    L.solo_set_contacts.argtypes = [vp, fp, vp]
     L.solo_get_work_counters.argtypes = [vp, fp, vp]
     L.solo_forward_dynamics.argtypes = [vp, fp, fp, fp, vp]
     L.solo_substep.argtypes = [vp, fp, vp]

@@ -229,7 +229,7 @@ def train(args, config, env_constructor=SoloBaseEnv, writer=None):
         else:
             with torch.no_grad():
                 action = policy.select_action(obs) + float(args.expl_noise) * torch.randn(N, action_dim, device=device)
-        next_obs, rewards, dones, _infos = envs.step(action)
+        next_obs, rewards, dones, _infos = envs.step_inplace(action)      # copied into the replay ring right below
         tracker.update(sim, dones)
         replay.append_batch(obs, action, rewards, next_obs, 1.0 - dones)
         obs.copy_(next_obs)

@@ -91,7 +91,7 @@ class Rollout:
         for t in range(self.T):
             with torch.no_grad():
                 value, action, logp = self.ac.act(self.buf.obs[t])
-                obs, reward, done, _infos = self.envs.step(action)
+                obs, reward, done, _infos = self.envs.step_inplace(action)    # copied into buf right below
                 self.tracker.update(self.sim, done)
                 self.buf.append(obs, action, logp, value, reward, (1.0 - done).unsqueeze(-1))
 
@@ -145,14 +145,14 @@ def train(args, config, env_constructor=SoloBaseEnv, writer=None):
     envs = make_vec_envs(config, N, env_constructor, args.gamma, device, seed=args.seed,
                          env_id_offset=rank * N)
     action_dim = envs.action_space.shape[0]
-    base = torch.load(args.base_checkpoint) if args.base_checkpoint is not None else None
+    base = torch.load(args.base_checkpoint, map_location=device) if args.base_checkpoint is not None else None
     actor_critic = Policy(envs.observation_space.shape, envs.action_space, base, {"hidden_size": args.hidden_size})
     actor_critic.to(device)
     broadcast_parameters(actor_critic)
     agent = PPO(actor_critic, args.clip_param, args.ppo_epoch, args.mini_batch_size, args.value_loss_coef,
                 args.entropy_coef, lr=args.lr, l2_coef=args.l2_coef, max_grad_norm=args.max_grad_norm)
     buf = OPBuffer(num_steps, N, envs.observation_space.shape, action_dim, device)
-    buf.obs[0].copy_(envs.reset())
+    buf.obs[0].copy_(envs.reset_inplace())
     tracker = EpisodeTracker(device)
     rollout = Rollout(envs, actor_critic, buf, tracker, num_steps, use_graph=getattr(args, "cuda_graph", True))
 
@@ -205,6 +205,12 @@ def train(args, config, env_constructor=SoloBaseEnv, writer=None):
                 stop = True
             if args.max_seconds is not None and elapsed >= args.max_seconds:
                 stop = True
+            if dist_ready():
+                # every rank must leave the loop at the same update: `elapsed` is a per-rank clock, and a rank
+                # that stopped alone would leave the others waiting in the next gradient all-reduce
+                flag = torch.tensor([1.0 if stop else 0.0], device=device)
+                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+                stop = bool(flag.item() > 0.5)
         if stop:
             break
     if args.logdir is not None and rank == 0:

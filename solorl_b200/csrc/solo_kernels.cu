@@ -53,8 +53,12 @@ struct DevArrays {
   float* rc_qd;
   float* rc_cforce;  /* [K][4] */
   float* rc_hist;    /* [K][H][D0] */
+  /* run-time mutable scalars, read by the kernels from device memory so that a captured CUDA graph of the
+   * step sees later updates: [0] = pointgoal goal radius (increment_goal_radius, solo.py:332-334) */
+  const float* mut;
   int cap;
 };
+enum { kMutGoalRadius = 0, kMutCount = 4 };
 
 struct StepArgs {
   DevArrays d;
@@ -68,7 +72,6 @@ struct StepArgs {
   float* done;
   uint32_t seed_lo, seed_hi;
   long long env_id_offset;
-  float goal_radius;
   int reset_simulate; /* 1: done envs restart from the reset pose with settle_left = k */
   int force_settle;   /* >=0: cache generation, env i settles settle_min + i steps, goal far away */
 };
@@ -81,7 +84,6 @@ struct ResetArgs {
   float* obs;
   uint32_t seed_lo, seed_hi;
   long long env_id_offset;
-  float goal_radius;
   int reset_simulate, force_settle;
 };
 
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
       bk.goals += 1;
       uint32_t w[4];
       env_rng(args.seed_lo, args.seed_hi, gid, bk, w);
-      sample_goal(w, args.goal_radius, goal);
+      sample_goal(w, d.mut[kMutGoalRadius], goal);
     }
   }
 
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
       }
       /* worker auto-reset (agents/ppo/envs.py:38-40) */
       if (valid) {
-        begin_reset<NJL>(d, sc, D0, e, leg, gid, args.seed_lo, args.seed_hi, args.goal_radius,
+        begin_reset<NJL>(d, sc, D0, e, leg, gid, args.seed_lo, args.seed_hi, d.mut[kMutGoalRadius],
                          args.reset_simulate, -1, st, ln, cforce, goal, potential, bk);
         if (!args.reset_simulate) {
           make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
@@ -782,7 +784,7 @@ __global__ void reset_kernel(const __grid_constant__ ResetArgs args) {
   float cforce;
   EnvBook bk = d.book[e];
   begin_reset<NJL>(d, args.sc, args.D0, e, leg, args.env_id_offset + e, args.seed_lo, args.seed_hi,
-                   args.goal_radius, args.reset_simulate, args.force_settle, st, ln, cforce, goal, potential, bk);
+                   d.mut[kMutGoalRadius], args.reset_simulate, args.force_settle, st, ln, cforce, goal, potential, bk);
   if (!args.reset_simulate && args.obs != nullptr) {
     RowPieces<NJL> cur;
     make_pieces<NJL>(args.sc, st, ln, cforce, goal, cur);
@@ -877,6 +879,13 @@ __global__ void set_goal_kernel(DevArrays d, int n, const float* goals) {
   b[kBaseGoal] = goals[2 * e]; b[kBaseGoal + 1] = goals[2 * e + 1];
   float dx = b[0] - goals[2 * e], dy = b[1] - goals[2 * e + 1];
   b[kBasePot] = sqrtf(dx * dx + dy * dy);
+}
+
+/* parity hook: overwrite the per-foot contact record (normal force, < 0 = no contact point) */
+__global__ void set_contacts_kernel(DevArrays d, int n, const float* force) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 4) return;
+  d.cforce[t] = force[t];
 }
 
 __global__ void work_kernel(DevArrays d, int n, int* out) {
@@ -1085,7 +1094,7 @@ static StepArgs make_step_args(SoloHandle* h, int mode, int n, const float* in, 
   a.D0 = h->D0; a.D = h->D; a.A = h->A;
   a.in = in; a.obs = obs; a.reward = rew; a.done = done;
   a.seed_lo = (uint32_t)(h->seed & 0xffffffffu); a.seed_hi = (uint32_t)(h->seed >> 32);
-  a.env_id_offset = h->env_id_offset; a.goal_radius = h->goal_radius;
+  a.env_id_offset = h->env_id_offset;
   a.reset_simulate = (h->params.reset_mode == SOLO_RESET_SIMULATE);
   a.force_settle = -1;
   return a;
@@ -1116,7 +1125,7 @@ static ResetArgs make_reset_args(SoloHandle* h, int n, const uint8_t* mask, floa
   a.d = h->d; a.sc = h->sc; a.n = n; a.njl = h->njl; a.D0 = h->D0; a.D = h->D;
   a.mask = mask; a.obs = obs;
   a.seed_lo = (uint32_t)(h->seed & 0xffffffffu); a.seed_hi = (uint32_t)(h->seed >> 32);
-  a.env_id_offset = h->env_id_offset; a.goal_radius = h->goal_radius;
+  a.env_id_offset = h->env_id_offset;
   a.reset_simulate = (h->params.reset_mode == SOLO_RESET_SIMULATE);
   a.force_settle = -1;
   return a;
@@ -1166,10 +1175,13 @@ int solo_destroy(SoloHandle* h) {
   cudaFree(h->d.base); cudaFree(h->d.q); cudaFree(h->d.qd); cudaFree(h->d.cforce); cudaFree(h->d.hist);
   cudaFree(h->d.book); cudaFree(h->d.stats);
   cudaFree(h->d.rc_base); cudaFree(h->d.rc_q); cudaFree(h->d.rc_qd); cudaFree(h->d.rc_cforce); cudaFree(h->d.rc_hist);
+  cudaFree(const_cast<float*>(h->d.mut));
   cudaFree(h->s_act); cudaFree(h->s_obs); cudaFree(h->s_rew); cudaFree(h->s_done);
   delete h;
   return SOLO_OK;
 }
+
+static int allocate_and_prime(SoloHandle* h, const SoloSimParams* params);
 
 int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_t num_envs, int32_t device,
                 uint64_t seed, int64_t env_id_offset, SoloHandle** out) {
@@ -1202,9 +1214,29 @@ int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_
   { const char* ev = getenv("SOLO_HOST_ZERO_COPY"); h->host_zero_copy = !(ev && ev[0] == '0'); }
   memset(&h->d, 0, sizeof(h->d));
   h->d.cap = h->cap;
+  rc = allocate_and_prime(h, params);
+  if (rc != SOLO_OK) {            /* no leak on a failed create: free whatever was allocated */
+    const std::string msg = h->err;
+    solo_destroy(h);
+    return fail(nullptr, rc, msg);
+  }
+  *out = h;
+  return SOLO_OK;
+}
+
+}  // extern "C"
+
+static int allocate_and_prime(SoloHandle* h, const SoloSimParams* params) {
   const int H = params->num_history_stack;
-  CUDA_TRY(h, cudaSetDevice(device));
+  CUDA_TRY(h, cudaSetDevice(h->device));
   const size_t cap = (size_t)h->cap;
+  {
+    float* mut = nullptr;
+    CUDA_TRY(h, cudaMalloc(&mut, kMutCount * sizeof(float)));
+    h->d.mut = mut;
+    const float init[kMutCount] = {h->goal_radius, 0.f, 0.f, 0.f};
+    CUDA_TRY(h, cudaMemcpy(mut, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(h, cudaMalloc(&h->d.base, cap * kBaseStride * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d.q, cap * 4 * h->njl * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d.qd, cap * 4 * h->njl * sizeof(float)));
@@ -1240,8 +1272,9 @@ int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_
       a.reset_simulate = 1;
       launch_step(h, a, s);
     }
-    if (h->njl == 3) fill_cache_kernel<3><<<1, 32, 0, s>>>(h->d, h->K, H, h->D0);
-    else fill_cache_kernel<2><<<1, 32, 0, s>>>(h->d, h->K, H, h->D0);
+    const int fc_blocks = (h->K + 31) / 32;   /* any settle span, not just the default 7 rows */
+    if (h->njl == 3) fill_cache_kernel<3><<<fc_blocks, 32, 0, s>>>(h->d, h->K, H, h->D0);
+    else fill_cache_kernel<2><<<fc_blocks, 32, 0, s>>>(h->d, h->K, H, h->D0);
     h->launches++;
     /* the cache-generation envs leave no trace: counters, goals and states start from zero */
     CUDA_TRY(h, cudaMemsetAsync(h->d.book, 0, cap * sizeof(EnvBook), s));
@@ -1253,9 +1286,10 @@ int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_
     CUDA_TRY(h, cudaStreamSynchronize(s));
     CUDA_TRY(h, cudaGetLastError());
   }
-  *out = h;
   return SOLO_OK;
 }
+
+extern "C" {
 
 int solo_reset(SoloHandle* h, const uint8_t* d_mask, float* d_obs_out, void* stream) {
   if (!h) return fail(nullptr, SOLO_E_ARG, "null handle");
@@ -1376,6 +1410,14 @@ int solo_get_contacts(SoloHandle* h, float* d_out, void* stream) {
   return SOLO_OK;
 }
 
+int solo_set_contacts(SoloHandle* h, const float* d_force, void* stream) {
+  if (!h || !d_force) return fail(h, SOLO_E_ARG, "null argument");
+  set_contacts_kernel<<<(h->n * 4 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d, h->n, d_force);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
 int solo_get_work_counters(SoloHandle* h, int32_t* d_out, void* stream) {
   if (!h || !d_out) return fail(h, SOLO_E_ARG, "null argument");
   work_kernel<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d, h->n, d_out);
@@ -1457,6 +1499,14 @@ int solo_accumulate_episode_stats(SoloHandle* h, const float* d_done, double* d_
 int solo_set_goal_radius(SoloHandle* h, double goal_radius) {
   if (!h) return fail(nullptr, SOLO_E_ARG, "null handle");
   h->goal_radius = (float)goal_radius;
+  /* The radius lives in device memory (DevArrays::mut) because a step captured into a CUDA graph bakes its
+   * kernel parameters: a by-value radius would stay at its capture-time value.  The call has no stream
+   * argument and is rare (one curriculum increment per so many updates), so it simply orders itself after
+   * everything in flight on the device and writes synchronously. */
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  CUDA_TRY(h, cudaMemcpy(const_cast<float*>(h->d.mut) + kMutGoalRadius, &h->goal_radius, sizeof(float),
+                         cudaMemcpyHostToDevice));
   return SOLO_OK;
 }
 

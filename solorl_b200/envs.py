@@ -52,15 +52,26 @@ class LazyInfos:
     episode ended at this step and ``{}`` otherwise (nobody reads non-terminal infos:
     agents/ppo/train.py:90-100, agents/td3/train.py:108-115)."""
 
-    def __init__(self, sim: SoloSim, done: torch.Tensor):
-        self._sim, self._done = sim, done
+    def __init__(self, sim: SoloSim, done: torch.Tensor, snapshot: bool = True):
+        """snapshot=True (the public step()): the done flags and the episode records are copied on the
+        device NOW (two small device-to-device copies, no host sync), so that an infos object inspected
+        after later steps still describes ITS step; snapshot=False reads the live buffers lazily (the
+        in-repo rollout, which never looks at infos)."""
+        self._sim = sim
         self._rec = None
         self._done_np = None
+        if snapshot:
+            self._done = done.detach().clone()
+            self._stats = sim.episode_stats_snapshot()
+        else:
+            self._done, self._stats = done, None
 
     def _fetch(self):
-        if self._rec is None:
+        if self._done_np is None:
             self._done_np = self._done.detach().cpu().numpy() > 0.5
-            self._rec = self._sim.episode_stats() if self._done_np.any() else None
+            if self._done_np.any():
+                self._rec = (self._sim.episode_stats() if self._stats is None
+                             else self._stats.cpu().numpy().view(self._sim.stats_dtype))
         return self._rec
 
     @staticmethod
@@ -129,11 +140,15 @@ class SoloVecEnv:
         self.closed = False
 
     def reset(self):
+        """The handle's persistent observation buffer (overwritten by the next reset/step): the zero-copy call
+        of the in-repo trainers.  ``PyTorchEnvWrapper`` hands out copies."""
         return self.sim.reset()
 
-    def step(self, actions):
+    def step(self, actions, snapshot: bool = False):
+        """Returns the handle's persistent obs / reward / done buffers (overwritten by the next step) and a
+        lazy infos object; ``snapshot=True`` freezes the infos of this step (see LazyInfos)."""
         obs, rew, done = self.sim.step(actions)
-        return obs, rew, done, LazyInfos(self.sim, done)
+        return obs, rew, done, LazyInfos(self.sim, done, snapshot=snapshot)
 
     def get_observation(self):
         return self.sim.get_observation()
@@ -172,8 +187,8 @@ class VecNormalize:
         self.ret = torch.zeros(self.nenvs, dtype=torch.float32, device=venv.device)
         self.training = True
 
-    def step(self, actions):
-        obs, rews, news, infos = self.venv.step(actions)
+    def step(self, actions, **kw):
+        obs, rews, news, infos = self.venv.step(actions, **kw)
         # in place, so that a CUDA graph captured around step() keeps updating the same tensor
         self.ret.mul_(self.gamma).add_(rews)               # running_mean_std.py:98
         self.ret.mul_((news <= 0.5).to(self.ret.dtype))    # :105
@@ -200,7 +215,14 @@ class VecNormalize:
 
 class PyTorchEnvWrapper:
     """``agents/ppo/envs.py:183-222``: same return shapes (obs [N,D] f32, reward [N,1] f32,
-    done [N] f32, infos sequence), tensors already on the device."""
+    done [N] f32, infos sequence), tensors already on the device.
+
+    ``step`` / ``reset`` return FRESH tensors, like the reference's ``torch.from_numpy(...).to(device)``
+    (envs.py:192-196): a caller may keep ``obs`` next to ``next_obs`` (the TD3/SAC pattern
+    ``buffer.append(obs, a, r, next_obs, 1 - done); obs = next_obs``) and inspect ``infos`` later.  The
+    copies are three small device-to-device launches; ``step_inplace`` / ``reset_inplace`` are the
+    zero-copy calls the in-repo trainers use (they copy into their own buffers right away) and return
+    the handle's persistent buffers, which the next call overwrites."""
 
     def __init__(self, envs, device):
         self.envs = envs
@@ -208,10 +230,17 @@ class PyTorchEnvWrapper:
         self.device = device
 
     def step(self, actions):
+        ob, rw, done, info = self.envs.step(actions, snapshot=True)
+        return ob.clone(), rw.unsqueeze(-1).clone(), done.clone(), info
+
+    def step_inplace(self, actions):
         ob, rw, done, info = self.envs.step(actions)
         return ob, rw.unsqueeze(-1), done, info
 
     def reset(self):
+        return self.envs.reset().clone()
+
+    def reset_inplace(self):
         return self.envs.reset()
 
     def close(self):
@@ -281,7 +310,7 @@ def make_vec_envs(config, num_envs, env_constructor=SoloBaseEnv, gamma=0.99,
         device = torch.device("cuda", torch.cuda.current_device())
     if name == "SoloGaitEnvContact":
         from .gait import SoloGaitVecEnv
-        envs = SoloGaitVecEnv(config, num_envs, device=device, seed=seed)
+        envs = SoloGaitVecEnv(config, num_envs, device=device, seed=seed, env_id_offset=env_id_offset)
     else:
         envs = SoloVecEnv(config, num_envs, device=device, seed=seed, env_id_offset=env_id_offset)
     envs = VecNormalize(envs, ob=False, ret=False, clipob=100, cliprew=100, gamma=gamma)

@@ -190,8 +190,10 @@ class SoloGaitVecEnv:
 
     OBS_DIM = 64          # soloGaitEnvContact.py:36-38
 
-    def __init__(self, config, num_envs, device=None, seed=0, controller_factory=None, cuda_graph=True):
+    def __init__(self, config, num_envs, device=None, seed=0, controller_factory=None, cuda_graph=True,
+                 env_id_offset=0):
         self.config = dict(config)
+        self.env_id_offset = int(env_id_offset)
         self.dt = float(config.get("dt", 0.002))                       # baseControlEnv.py:37
         self.T_gait = float(config.get("T_gait", 0.32))
         self.rl_dt = self.T_gait / 2                                   # soloGaitEnvContact.py:27-28
@@ -218,7 +220,9 @@ class SoloGaitVecEnv:
         self.observation_space = Box(-np.inf * np.ones(self.OBS_DIM), np.inf * np.ones(self.OBS_DIM))
         f = dict(dtype=torch.float32, device=dev)
         self.gait_table = torch.tensor(GAIT_TABLE, **f)
-        self.gen = torch.Generator(device=dev).manual_seed(seed)
+        # one stream per shard: ranks of a multi-GPU run (env_id_offset = rank * N) must not draw identical
+        # velocity references / pushes
+        self.gen = torch.Generator(device=dev).manual_seed(int(seed) * 1000003 + self.env_id_offset)
         self.timestep = torch.zeros(self.nenvs, dtype=torch.int32, device=dev)
         self.past_gaits = torch.full((self.nenvs, 3), 9, dtype=torch.long, device=dev)     # deque([-1,-1,-1])
         self.vel_ref = torch.zeros(self.nenvs, 6, **f)
@@ -278,7 +282,7 @@ class SoloGaitVecEnv:
         self._was_reset = True
         return self.get_observation()
 
-    def step(self, action):
+    def step(self, action, snapshot=False):
         assert self._was_reset, "env.reset() must be called before step"          # baseControlEnv.py:135
         a = torch.as_tensor(action, device=self.device).long().reshape(self.nenvs)
         self.past_gaits = torch.cat([self.past_gaits[:, 1:], a.unsqueeze(1)], dim=1)   # soloGaitEnvContact.py:42

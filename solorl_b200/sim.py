@@ -95,6 +95,14 @@ class SoloSim:
         _lib.check(self.L.solo_episode_stats(self.h, _ptr(self._stats), self._stream()), self.h)
         return self._stats.cpu().numpy().view(EPISODE_STATS_DTYPE)
 
+    stats_dtype = EPISODE_STATS_DTYPE
+
+    def episode_stats_snapshot(self):
+        """A private device copy of the current episode records (uint8 bytes of SoloEpisodeStats[N]); no sync."""
+        out = torch.empty_like(self._stats)
+        _lib.check(self.L.solo_episode_stats(self.h, _ptr(out), self._stream()), self.h)
+        return out
+
     def episode_stats_device(self):
         """The same records without leaving the device: (float32 view [N,12], int32 view [N,12]) of
         ``SoloEpisodeStats[N]``; columns 0,1,6..10 are floats (episode_reward, episode_return, dr/*),
@@ -127,6 +135,11 @@ class SoloSim:
     def set_goals(self, goals):
         g = self._f32(goals, (self.n, 2))
         _lib.check(self.L.solo_set_goals(self.h, _ptr(g), self._stream()), self.h)
+
+    def set_contacts(self, force):
+        """Inject the per-foot contact record (normal force [N,4], negative = no contact point)."""
+        f = self._f32(force, (self.n, 4))
+        _lib.check(self.L.solo_set_contacts(self.h, _ptr(f), self._stream()), self.h)
 
     def get_contacts(self):
         out = torch.empty(self.n, 4, 3, dtype=torch.float32, device=self.device)
