@@ -125,47 +125,112 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline(seconds=12.0, nthreads=None):
-    """The oracle port on all host threads over a bounded sample of the same workload."""
-    from oracle.oracle import OracleVecEnv, lib
+CPU_RESET_NOTE = ("resets simulated: every auto-reset runs its 5..11 zero-torque settle steps, as the reference does "
+                  "(baseEnv.py:79-80); the GPU arm looks the same trajectories up in its reset cache (bit-identical, "
+                  "reset_mode 'cached') and reports the simulate-mode figure under 'reset_mode_simulate'")
+
+
+def pin_rank_to_cores(local, world):
+    """One core set per rank.  The ranks of a torchrun job inherit the SAME affinity mask (all eight ranks of the
+    round-1 scaling run shared CPUs 0-31), and each spins in a stream synchronise once per host-buffer step, so
+    they fought over cores: e2e efficiency 0.92 at N = 8 with the device figure at 0.99."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        if world <= 1 or len(cpus) < world:
+            return len(cpus)
+        per = len(cpus) // world
+        mine = cpus[local * per:(local + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except Exception:
+        return None
+
+
+def make_cpu_env(n, nthreads):
+    from oracle.oracle import OracleVecEnv
     from solorl_b200.abi import params_from_config
     from solorl_b200.model import SoloModel
     m = SoloModel.resolve(CONFIG["model_urdf"])
     p = params_from_config(CONFIG, m)
-    nthreads = nthreads or host_threads()
-    n = 32 * nthreads
     v = OracleVecEnv(m, p, n, seed=1, nthreads=nthreads)
     v.reset()
     rng = np.random.default_rng(1)
     acts = [rng.uniform(-1, 1, size=(n, v.act_dim)).astype(np.float32) for _ in range(8)]
-    for i in range(3):
+    return v, acts
+
+
+def cpu_baseline(seconds=12.0, nthreads=None, n=ENVS_PER_GPU):
+    """The oracle port on all host threads, stepping the SAME batch as the GPU arm (all `n` envs per step) for a
+    bounded time."""
+    nthreads = nthreads or host_threads()
+    v, acts = make_cpu_env(n, nthreads)
+    for i in range(2):
         v.step(acts[i])
     t0, steps = time.perf_counter(), 0
-    while time.perf_counter() - t0 < seconds:
+    while time.perf_counter() - t0 < seconds or steps < 3:
         v.step(acts[steps % 8])
         steps += 1
     dt = time.perf_counter() - t0
     return {"value": n * steps / dt, "unit": "env-steps/s", "cores": nthreads, "kind": "port",
             "sample": f"{n} envs x {steps} steps ({dt:.1f} s) of the same workload; fp64 CPU restatement "
-                      f"(oracle/), not PyBullet (not installable in this image)"}
+                      f"(oracle/), not PyBullet (not installable in this image); " + CPU_RESET_NOTE}
+
+
+def pybullet_direct_baseline(seconds=30.0):
+    """the reference's own vec-env on PyBullet DIRECT, one worker process per host core, random
+    actions as in agents/td3/train.py:98.  Needs pybullet / gym / pybullet_envs and a checkout of the reference
+    (SOLORL_REFERENCE, baseline/_ref/soloRL or /root/reference); returns (result, reason)."""
+    try:
+        import pybullet  # noqa: F401
+        import gym  # noqa: F401
+    except Exception as e:
+        return None, f"pybullet not installed ({type(e).__name__})"
+    ref = None
+    for cand in (os.environ.get("SOLORL_REFERENCE"), os.path.join(ROOT, "baseline", "_ref", "soloRL"), "/root/reference"):
+        if cand and os.path.exists(os.path.join(cand, "baseEnv.py")):
+            ref = os.path.abspath(cand)
+            break
+    if ref is None:
+        return None, "no checkout of the reference found (set SOLORL_REFERENCE)"
+    try:
+        import tempfile
+        import torch
+        parent, name = os.path.split(ref.rstrip("/"))
+        if name != "soloRL":
+            parent = tempfile.mkdtemp(prefix="solorl_ref_")
+            os.symlink(ref, os.path.join(parent, "soloRL"))
+        sys.path.insert(0, parent)
+        from soloRL.agents.ppo.envs import make_vec_envs as ref_make_vec_envs
+        from soloRL.baseEnv import SoloBaseEnv as RefEnv
+        cfg = dict(CONFIG, model_urdf=os.path.join(ref, "solo_description", "robots", "solo12.urdf"), mode="direct")
+        n = host_threads()
+        envs = ref_make_vec_envs(cfg, n, RefEnv, 0.99, torch.device("cpu"))
+        envs.reset()
+        A = envs.action_space.shape[0]
+        for _ in range(100):
+            envs.step(torch.randn(n, A))
+        t0, steps = time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds:
+            envs.step(torch.randn(n, A))
+            steps += 1
+        dt = time.perf_counter() - t0
+        envs.close()
+        return {"value": n * steps / dt, "unit": "env-steps/s", "cores": n, "kind": "reference",
+                "sample": f"{n} PyBullet DIRECT worker processes x {steps} steps ({dt:.1f} s), reference code unmodified"}, None
+    except Exception as e:
+        return None, f"reference vec-env failed: {e!r}"[:300]
 
 
 def run_reference(args):
-    """CPU arm.  Rank 0 alone runs; a step = one vec step of a bounded sample (32 envs per thread)."""
+    """CPU arm.  Rank 0 alone runs; a step = one vec step of ALL `--envs` envs (the GPU arm's batch), on every
+    host thread this process may use (own pthread pool: independent of the OMP_NUM_THREADS=1 torchrun exports)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.oracle import OracleVecEnv, lib
-    from solorl_b200.abi import dims, params_from_config
-    from solorl_b200.model import SoloModel
-    m = SoloModel.resolve(CONFIG["model_urdf"])
-    p = params_from_config(CONFIG, m)
     nthreads = host_threads()
-    n = 32 * nthreads
-    v = OracleVecEnv(m, p, n, seed=1, nthreads=nthreads)
-    v.reset()
-    rng = np.random.default_rng(1)
-    acts = [rng.uniform(-1, 1, size=(n, v.act_dim)).astype(np.float32) for _ in range(8)]
+    n = args.envs
+    pyb, reason = pybullet_direct_baseline(20.0)
+    v, acts = make_cpu_env(n, nthreads)
     for i in range(args.warmup):
         v.step(acts[i % 8])
     t0 = time.perf_counter()
@@ -173,15 +238,19 @@ def run_reference(args):
         v.step(acts[i % 8])
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
-    sample = (f"{n} envs per step on {nthreads} host threads (bounded sample of the {ENVS_PER_GPU}-env workload); "
-              f"fp64 CPU restatement (oracle/), PyBullet itself is not installable in this image")
+    sample = (f"{n} envs per step (the GPU arm's batch) on {nthreads} host threads; fp64 CPU restatement (oracle/), "
+              f"PyBullet itself is not installable in this image; " + CPU_RESET_NOTE)
     line = {"impl": "reference", "metric": "env-steps/sec", "value": val, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_step": n, "robot": "solo12", "task": "walk"},
+            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "envs_per_step": n, "robot": "solo12", "task": "walk",
+                       "control": "torque", "num_history_stack": 1, "episode_length": 400, "solver_iters": 50,
+                       "solver_residual_threshold": 1e-7, "reset_mode": "simulate"},
             "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": nthreads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "pybullet_direct": None, "reason": "pybullet not installed"}
+            "pybullet_direct": pyb, "reason": reason}
+    if pyb is not None:       # the reference itself ran: it is the arm
+        line.update(value=pyb["value"], cpu_baseline=pyb, e2e=dict(line["e2e"], value=pyb["value"]))
     print(json.dumps(line), flush=True)
 
 
@@ -247,11 +316,82 @@ def time_saturated(cfg, dev, n, steps=60):
             "flops_per_env_step": algorithmic_flops_per_env_step(nj, float(np.mean(ncs)), float(np.mean(sws)))}
 
 
+def time_reset_simulate(cfg, n, dev, steps=40):
+    """The headline workload with reset_mode 'simulate' (settle steps run in the step path, what the CPU arms and
+    the reference do) instead of the bit-identical reset cache."""
+    import torch
+    from solorl_b200.envs import SoloVecEnv
+    env = SoloVecEnv(dict(cfg, reset_mode="simulate"), n, device=dev, seed=1)
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(11)
+    acts = [torch.rand(n, env.sim.act_dim, device=dev, generator=g) * 2 - 1 for _ in range(8)]
+    for i in range(20):
+        env.sim.step(acts[i % 8])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = env.sim.launch_count
+    e0.record()
+    for i in range(steps):
+        env.sim.step(acts[i % 8])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": n / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
+           "launches_per_step": (env.sim.launch_count - l0) / steps,
+           "what": "device-resident, back-to-back steps, settle steps simulated after every auto-reset"}
+    env.close()
+    return out
+
+
+def time_gae(dev, peaks, T=400, N=ENVS_PER_GPU, reps=20):
+    """HBM view of the rollout-buffer kernel (solo_gae): 20 B per (t, env)."""
+    import torch
+    from solorl_b200.sim import gae
+    g = torch.Generator(device=dev).manual_seed(3)
+    r = torch.randn(T, N, device=dev, generator=g)
+    v = torch.randn(T + 1, N, device=dev, generator=g)
+    m = (torch.rand(T + 1, N, device=dev, generator=g) > 0.02).float()
+    ret = torch.zeros(T + 1, N, device=dev)
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    for _ in range(3):
+        gae(r, v, m, ret, 0.99, 0.95, True)
+    tot = 0.0
+    for i in range(reps):
+        flush.fill_(float(i))            # the 33 MB of the rollout would otherwise sit in the 126 MB L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gae(r, v, m, ret, 0.99, 0.95, True)
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    ms = tot / reps
+    gbs = 20.0 * T * N / (ms * 1e-3) / 1e9
+    peak = peaks.get("hbm_gbs", 6650.0)
+    return {"kernel": "gae_chunked_kernel", "T": T, "N": N, "ms": ms, "bound": "hbm", "achieved": gbs, "peak": peak,
+            "unit": "GB/s", "frac": gbs / peak, "algorithmic_bytes": 20 * T * N, "l2": "flushed between launches"}
+
+
+def measured_traffic(n, variant):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE step_kernel launch from the committed `ncu --set full`
+    capture of this workload (profiles/step_kernel_traffic.json names the commit and the command); None when no
+    capture matches the batch size and kernel build of this run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
+            recs = json.load(f)["captures"]
+        for r in recs:
+            if r["envs"] == n and r["build"] == variant:
+                return r["dram_bytes_read"] + r["dram_bytes_write"], r["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def run_ours(args):
     import torch
     from solorl_b200 import _lib, build
     from solorl_b200.envs import SoloVecEnv
     rank, world, local = dist_setup(args.gpus)
+    cores = pin_rank_to_cores(local, world)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     _lib.lib()   # fail loudly if the extension is missing
@@ -386,12 +526,12 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     abytes = algorithmic_bytes_per_env_step(nj, D) * n
+    variant = sim.step_variant
+    traffic, traffic_src = measured_traffic(n, variant)
     roofline = {
-        "bound": "fp32", "kernel": "step_kernel<3>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "bound": "fp32", "kernel": "step kernel, build '%s'" % variant, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this workload
-        # (profiles/r1j_step_kernel_ncu_full.txt); only valid for the default 4096-env Solo12 workload
-        "traffic": 1298432 if (n == ENVS_PER_GPU) else None,
+        "traffic": traffic, "traffic_source": traffic_src,
         "traffic_unit": "bytes per launch (algorithmic: %d)" % (algorithmic_bytes_per_env_step(nj, D) * n),
         "peak_source": "FP32 FMA microbenchmark measured live in this run (solo_bench_fma_peak)" if rc == 0
         else "fallback 148 SM x 128 lanes x 2 x 1.965 GHz",
@@ -410,7 +550,8 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n, "robot": "solo12", "task": "walk", "control": "torque",
                    "num_history_stack": 1, "episode_length": 400, "solver_iters": 50,
-                   "solver_residual_threshold": 1e-7, "reset_mode": "cached", "step_kernel_build": "latency" if n <= 8192 else "throughput",
+                   "solver_residual_threshold": 1e-7, "reset_mode": "cached", "step_kernel_build": variant,
+                   "host_cores_of_this_rank": cores,
                    "l2": "flushed (256 MiB write) between timed steps; per-step CUDA events summed",
                    "parallelism": f"env-shard x{world}"},
         "clocks": clocks, "gpu_launches": int(launches),
@@ -425,13 +566,18 @@ def run_ours(args):
     if saturated and "flops_per_env_step" in saturated:
         ach = saturated["flops_per_env_step"] * saturated["value"] / 1e12
         saturated.update({"achieved_tflops": ach, "peak_tflops": peak, "frac": ach / peak})
+    if world == 1:
+        try:
+            line["reset_mode_simulate"] = time_reset_simulate(cfg, n, dev)
+        except Exception as e:
+            line["reset_mode_simulate"] = {"error": repr(e)[:200]}
+        try:
+            line["gae"] = time_gae(dev, peaks)
+        except Exception as e:
+            line["gae"] = {"error": repr(e)[:200]}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
-        try:                                    # the reference itself, if it ever becomes runnable here
-            import pybullet  # noqa: F401
-            line["pybullet_direct"] = "installed but not wired: see BASELINE.md B0"
-        except Exception:
-            line["pybullet_direct"], line["reason"] = None, "pybullet not installed"
+        line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, n=n)
+        line["pybullet_direct"], line["reason"] = pybullet_direct_baseline(20.0)   # SURVEY §8(d)(i) / BASELINE.md B0
     print(json.dumps(line), flush=True)
     env.close()
 

@@ -86,6 +86,7 @@ def lib():
         L.oracle_gae.argtypes = [fp, fp, fp, fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
         L.oracle_batch_reset.argtypes = [C.POINTER(vp), C.c_int, fp, C.c_int]
         L.oracle_batch_step.argtypes = [C.POINTER(vp), C.c_int, fp, fp, fp, fp, C.c_int]
+        L.oracle_batch_substep.argtypes = [C.POINTER(vp), C.c_int, dp, dp, dp, dp, C.POINTER(C.c_int), C.c_int]
         L.oracle_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -274,6 +275,17 @@ class OracleVecEnv:
         obs = np.zeros((self.n, self.d), np.float32)
         self.L.oracle_batch_reset(self.ptrs, self.n, _fp(obs), self.nthreads)
         return obs
+
+    def substep_from(self, states, taus):
+        """env i <- states[i], one substep with taus[i]: (next states, contacts [n,4,3], PGS sweeps [n])."""
+        s = np.ascontiguousarray(states, np.float64)
+        t = np.ascontiguousarray(taus, np.float64)
+        assert s.shape[0] == self.n and t.shape[0] == self.n
+        out, con = np.zeros_like(s), np.zeros((self.n, 4, 3))
+        it = np.zeros(self.n, np.int32)
+        self.L.oracle_batch_substep(self.ptrs, self.n, _dp(s), _dp(t), _dp(out), _dp(con),
+                                    it.ctypes.data_as(C.POINTER(C.c_int)), self.nthreads)
+        return out, con, it
 
     def step(self, actions):
         a = np.ascontiguousarray(actions, np.float32)

@@ -11,9 +11,6 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
-#ifdef _OPENMP
-#include <omp.h>
-#endif
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -1270,36 +1267,122 @@ void oracle_gae(const float* rewards, const float* values, const float* masks, f
 }
 
 /* ------------------------------------------------------------------ batched (CPU baseline) */
+/* A persistent pthread pool (no OpenMP): bench.py runs under torchrun at N > 1, which exports
+ * OMP_NUM_THREADS=1 to every rank; libgomp then keeps a one-thread pool and builds / tears down the other
+ * team threads in EVERY `parallel num_threads(n)` region, which cut the CPU arm to a third of its
+ * stand-alone rate in round 1.  Workers pull chunks of envs from an atomic counter (dynamic schedule: env
+ * steps differ in cost by the number of contacts, PGS sweeps and resets) and sleep on a condition variable
+ * between batches. */
+#include <pthread.h>
+#include <stdatomic.h>
+#include <unistd.h>
+
+typedef struct {
+  OracleEnv** envs; int n; const float* actions; float* obs; float* reward; float* done; int mode;
+  const double* states; const double* taus; double* out_states; double* out_contacts; int* out_iters;  /* mode 2 */
+} BatchJob;
+
+static struct {
+  pthread_t th[256];
+  int nth, started;
+  pthread_mutex_t mu;
+  pthread_cond_t go, fin;
+  unsigned long gen;
+  int running;
+  atomic_int next;
+  BatchJob job;
+} g_pool = {.mu = PTHREAD_MUTEX_INITIALIZER, .go = PTHREAD_COND_INITIALIZER, .fin = PTHREAD_COND_INITIALIZER};
+
+static void batch_run_chunks(const BatchJob* j) {
+  const int chunk = 4;
+  for (;;) {
+    int i0 = atomic_fetch_add(&g_pool.next, chunk);
+    if (i0 >= j->n) break;
+    int i1 = i0 + chunk < j->n ? i0 + chunk : j->n;
+    for (int i = i0; i < i1; i++) {
+      OracleEnv* e = j->envs[i];
+      double o[ORACLE_MAX_D0 * (1 + ORACLE_MAX_HIST)];
+      if (j->mode == 2) {            /* parity tests: set_state -> one substep -> get_state / contacts */
+        const int W = 13 + 2 * e->nj;
+        oracle_set_state(e, j->states + (size_t)i * W);
+        oracle_substep(e, j->taus + (size_t)i * e->nj);
+        oracle_get_state(e, j->out_states + (size_t)i * W);
+        if (j->out_contacts) oracle_get_contacts(e, j->out_contacts + (size_t)i * 12);
+        if (j->out_iters) j->out_iters[i] = e->last_iters;
+      } else if (j->mode == 0) {
+        oracle_env_reset(e, o);
+        if (j->obs) for (int k = 0; k < e->d; k++) j->obs[(size_t)i * e->d + k] = (float)o[k];
+      } else {
+        double a[MAXL + 2], r;
+        int d;
+        for (int k = 0; k < e->act_dim; k++) a[k] = j->actions[(size_t)i * e->act_dim + k];
+        oracle_env_step(e, a, 1, o, &r, &d, NULL);
+        if (j->obs) for (int k = 0; k < e->d; k++) j->obs[(size_t)i * e->d + k] = (float)o[k];
+        j->reward[i] = (float)r; j->done[i] = (float)d;
+      }
+    }
+  }
+}
+
+static void* pool_worker(void* arg) {
+  (void)arg;
+  unsigned long seen = 0;
+  for (;;) {
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.gen == seen) pthread_cond_wait(&g_pool.go, &g_pool.mu);
+    seen = g_pool.gen;
+    BatchJob job = g_pool.job;
+    pthread_mutex_unlock(&g_pool.mu);
+    batch_run_chunks(&job);
+    pthread_mutex_lock(&g_pool.mu);
+    if (--g_pool.running == 0) pthread_cond_signal(&g_pool.fin);
+    pthread_mutex_unlock(&g_pool.mu);
+  }
+  return NULL;
+}
+
+static void pool_run(const BatchJob* job, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.nth < nthreads - 1) {          /* the caller is the n-th worker */
+    if (pthread_create(&g_pool.th[g_pool.nth], NULL, pool_worker, NULL) != 0) break;
+    g_pool.nth++;
+  }
+  const int helpers = g_pool.nth < nthreads - 1 ? g_pool.nth : nthreads - 1;
+  g_pool.job = *job;
+  atomic_store(&g_pool.next, 0);
+  /* every pooled thread wakes on the broadcast; more threads than asked for only happens when an earlier
+   * call asked for more, and they all pull from the same counter, so the result does not depend on it */
+  g_pool.running = g_pool.nth;
+  g_pool.gen++;
+  pthread_cond_broadcast(&g_pool.go);
+  pthread_mutex_unlock(&g_pool.mu);
+  (void)helpers;
+  batch_run_chunks(job);
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.running > 0) pthread_cond_wait(&g_pool.fin, &g_pool.mu);
+  pthread_mutex_unlock(&g_pool.mu);
+}
+
 int oracle_max_threads(void) {
-#ifdef _OPENMP
-  return omp_get_max_threads();
-#else
-  return 1;
-#endif
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  return n > 0 ? (int)n : 1;
+}
+
+void oracle_batch_substep(OracleEnv** envs, int n, const double* states, const double* taus, double* out_states,
+                          double* out_contacts, int* out_iters, int nthreads) {
+  BatchJob j = {envs, n, NULL, NULL, NULL, NULL, 2, states, taus, out_states, out_contacts, out_iters};
+  pool_run(&j, nthreads);
 }
 
 void oracle_batch_reset(OracleEnv** envs, int n, float* obs, int nthreads) {
-  (void)nthreads;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-  for (int i = 0; i < n; i++) {
-    double o[ORACLE_MAX_D0 * (1 + ORACLE_MAX_HIST)];
-    oracle_env_reset(envs[i], o);
-    int D = envs[i]->d;
-    if (obs) for (int k = 0; k < D; k++) obs[(size_t)i * D + k] = (float)o[k];
-  }
+  BatchJob j = {envs, n, NULL, obs, NULL, NULL, 0, NULL, NULL, NULL, NULL, NULL};
+  pool_run(&j, nthreads);
 }
 
 void oracle_batch_step(OracleEnv** envs, int n, const float* actions, float* obs, float* reward,
                        float* done, int nthreads) {
-  (void)nthreads;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
-  for (int i = 0; i < n; i++) {
-    OracleEnv* e = envs[i];
-    double a[MAXL + 2], o[ORACLE_MAX_D0 * (1 + ORACLE_MAX_HIST)], r;
-    int d;
-    for (int k = 0; k < e->act_dim; k++) a[k] = actions[(size_t)i * e->act_dim + k];
-    oracle_env_step(e, a, 1, o, &r, &d, NULL);
-    if (obs) for (int k = 0; k < e->d; k++) obs[(size_t)i * e->d + k] = (float)o[k];
-    reward[i] = (float)r; done[i] = (float)d;
-  }
+  BatchJob j = {envs, n, actions, obs, reward, done, 1, NULL, NULL, NULL, NULL, NULL};
+  pool_run(&j, nthreads);
 }

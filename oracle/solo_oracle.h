@@ -99,6 +99,10 @@ void oracle_gae(const float* rewards, const float* values, const float* masks, f
 void oracle_batch_reset(OracleEnv** envs, int n, float* obs, int nthreads);
 void oracle_batch_step(OracleEnv** envs, int n, const float* actions, float* obs,
                        float* reward, float* done, int nthreads);
+/* parity tests at scale: env i <- states[i]; one substep with taus[i]; out_states[i], out_contacts[i][4][3]
+ * (flag, has_point, force), out_iters[i] = PGS sweeps used (any output may be NULL except out_states) */
+void oracle_batch_substep(OracleEnv** envs, int n, const double* states, const double* taus, double* out_states,
+                          double* out_contacts, int* out_iters, int nthreads);
 int oracle_max_threads(void);
 
 #ifdef __cplusplus

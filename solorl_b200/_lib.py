@@ -22,7 +22,7 @@ SYMBOLS = [
     "solo_set_state", "solo_set_goals", "solo_get_contacts", "solo_get_work_counters", "solo_forward_dynamics",
     "solo_substep", "solo_action_to_torque", "solo_episode_stats", "solo_set_goal_radius",
     "solo_gae", "solo_launch_count", "solo_actuator_step", "solo_get_feet",
-    "solo_accumulate_episode_stats", "solo_set_contacts",
+    "solo_accumulate_episode_stats", "solo_set_contacts", "solo_step_variant",
 ]
 
 
@@ -71,8 +71,10 @@ def lib():
     L.solo_gae.argtypes = [fp, fp, fp, fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, vp]
     L.solo_launch_count.argtypes = [vp]
     L.solo_launch_count.restype = C.c_int64
+    L.solo_step_variant.argtypes = [vp]
+    L.solo_step_variant.restype = C.c_char_p
     for name in SYMBOLS:
-        if name not in ("solo_last_error", "solo_launch_count"):
+        if name not in ("solo_last_error", "solo_launch_count", "solo_step_variant"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

@@ -232,7 +232,8 @@ def params_from_config(config: dict, model: Optional[SoloModel] = None) -> SoloS
     p.pointgoal_dt = p.frame_skip * p.dt
     if model is not None:
         p.joint_state_limit = model.joint_state_limit          # solo.py:109
-    for k in ("torque_hold", "solver_iters", "cone_friction", "joint_limits", "limit_rows_per_leg"):
+    for k in ("torque_hold", "solver_iters", "cone_friction", "joint_limits", "limit_rows_per_leg", "settle_min",
+              "settle_max"):
         if k in config:
             setattr(p, k, int(config[k]))
     for k in ("contact_erp", "contact_margin", "contact_slop", "friction", "lin_damping",

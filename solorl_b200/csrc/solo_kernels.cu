@@ -1024,8 +1024,68 @@ __global__ void episode_accumulate_kernel(const SoloEpisodeStats* __restrict__ s
   atomic_max_double(acc + 12, (double)s.episode_length);
 }
 
-/* Reverse-scan GAE (agents/ppo/storage.py:35-55): one thread per env walks t = T-1..0;
- * consecutive threads read consecutive words of every [t] row, 20 B per (t, env). */
+/* Reverse-scan GAE (agents/ppo/storage.py:35-55), HBM-bound: 20 B per (t, env) = 4 reads + 1 write of fp32.
+ * The recurrence A_t = delta_t + gamma lam m_{t+1} A_{t+1} is serial in t, but nothing it READS depends on it.
+ * One thread per env walking t = T-1..0 (round 1) therefore ran at the latency of one dependent load chain
+ * (4096 threads, a few loads in flight each).  Here a block owns kGaeEnvs consecutive envs and kGaeChunks
+ * time chunks: thread (c, e) first loads ITS chunk's rewards / values / masks into registers -- all
+ * kGaeChunks x kGaeEnvs x 3L loads of the block are independent and in flight together -- and then the
+ * chunks run the recurrence one after the other, newest first, handing the running (gae, v_next) pair to
+ * the next chunk through shared memory.  The arithmetic and its order are exactly those of the serial walk,
+ * so results are bit-identical to the round-1 kernel and to the oracle's storage.py-order loop. */
+constexpr int kGaeEnvs = 32;      /* one 128-byte line per [t] row and block */
+constexpr int kGaeChunks = 16;
+constexpr int kGaeMaxL = 32;      /* time steps per chunk held in registers: T <= 512 takes the chunked path */
+template <int L>
+__global__ void __launch_bounds__(kGaeEnvs * kGaeChunks)
+gae_chunked_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                   const float* __restrict__ masks, float* __restrict__ returns, int T, int N,
+                   float gamma, float lam, int use_gae) {
+  __shared__ float carry_a[kGaeEnvs], carry_v[kGaeEnvs];
+  const int e = threadIdx.x & (kGaeEnvs - 1), c = threadIdx.x / kGaeEnvs;
+  const int n = blockIdx.x * kGaeEnvs + e;
+  const bool valid = n < N;
+  const int nn = valid ? n : N - 1;
+  /* chunk c covers t in [t0, t1), chunk kGaeChunks-1 is the newest */
+  const int t0 = c * L, t1 = min(T, t0 + L);
+  float r[L], v[L], m[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) {
+    const int t = t0 + i;
+    const bool on = t < t1;
+    const int tt = on ? t : 0;
+    r[i] = on ? rewards[(size_t)tt * N + nn] : 0.f;
+    v[i] = (on && use_gae) ? values[(size_t)tt * N + nn] : 0.f;
+    m[i] = on ? masks[(size_t)(tt + 1) * N + nn] : 0.f;
+  }
+  if (c == kGaeChunks - 1) {
+    carry_a[e] = use_gae ? 0.f : returns[(size_t)T * N + nn];
+    carry_v[e] = use_gae ? values[(size_t)T * N + nn] : 0.f;
+  }
+  for (int turn = kGaeChunks - 1; turn >= 0; turn--) {
+    __syncthreads();
+    if (turn == c && t0 < t1) {
+      float acc = carry_a[e], v_next = carry_v[e];
+#pragma unroll
+      for (int i = L - 1; i >= 0; i--) {
+        if (t0 + i < t1) {
+          if (use_gae) {
+            const float delta = r[i] + gamma * v_next * m[i] - v[i];
+            acc = delta + gamma * lam * m[i] * acc;
+            if (valid) returns[(size_t)(t0 + i) * N + n] = acc + v[i];
+            v_next = v[i];
+          } else {
+            acc = acc * gamma * m[i] + r[i];
+            if (valid) returns[(size_t)(t0 + i) * N + n] = acc;
+          }
+        }
+      }
+      carry_a[e] = acc; carry_v[e] = v_next;
+    }
+  }
+}
+
+/* any T: the serial walk (one thread per env) */
 __global__ void gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                            const float* __restrict__ masks, float* __restrict__ returns, int T, int N,
                            float gamma, float lam, int use_gae) {
@@ -1514,12 +1574,27 @@ int solo_gae(const float* d_rewards, const float* d_values, const float* d_masks
              int32_t N, float gamma, float lam, int32_t use_gae, void* stream) {
   if (!d_rewards || !d_values || !d_masks || !d_returns || T <= 0 || N <= 0)
     return fail(nullptr, SOLO_E_ARG, "bad argument to solo_gae");
-  gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_rewards, d_values, d_masks, d_returns, T, N,
-                                                               gamma, lam, use_gae);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int blocks = (N + kGaeEnvs - 1) / kGaeEnvs, threads = kGaeEnvs * kGaeChunks;
+  const char* ev = getenv("SOLO_GAE_SERIAL");
+  const bool serial = (ev && ev[0] == '1') || T > kGaeChunks * kGaeMaxL;
+  if (serial)
+    gae_kernel<<<(N + 127) / 128, 128, 0, s>>>(d_rewards, d_values, d_masks, d_returns, T, N, gamma, lam, use_gae);
+  else if (T <= kGaeChunks * 8)
+    gae_chunked_kernel<8><<<blocks, threads, 0, s>>>(d_rewards, d_values, d_masks, d_returns, T, N, gamma, lam, use_gae);
+  else if (T <= kGaeChunks * 16)
+    gae_chunked_kernel<16><<<blocks, threads, 0, s>>>(d_rewards, d_values, d_masks, d_returns, T, N, gamma, lam, use_gae);
+  else
+    gae_chunked_kernel<kGaeMaxL><<<blocks, threads, 0, s>>>(d_rewards, d_values, d_masks, d_returns, T, N, gamma, lam, use_gae);
   if (cudaGetLastError() != cudaSuccess) return fail(nullptr, SOLO_E_CUDA, "gae_kernel launch failed");
   return SOLO_OK;
 }
 
 int64_t solo_launch_count(const SoloHandle* h) { return h ? h->launches : 0; }
+
+const char* solo_step_variant(const SoloHandle* h) {
+  if (!h) return "";
+  return h->throughput ? "throughput" : "latency";
+}
 
 }  // extern "C"

@@ -181,6 +181,10 @@ class SoloSim:
         return out
 
     @property
+    def step_variant(self):
+        return self.L.solo_step_variant(self.h).decode()
+
+    @property
     def launch_count(self):
         return int(self.L.solo_launch_count(self.h))
 

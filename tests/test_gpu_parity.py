@@ -17,6 +17,7 @@ from tests.helpers import flag_slots, GOLDEN, make_config, obs_diff, random_stat
 pytestmark = pytest.mark.gpu
 
 ROBOTS = ("solo8", "solo12")
+BUILDS = ("latency", "throughput")      # every build of the step kernel is held to the same bounds
 TOL_QDD = 1e-5
 TOL_ENV = 1e-6
 TOL_CONTACT = 1e-3
@@ -67,9 +68,18 @@ def test_action_to_torque_1e6(control):
     sim.set_state(cuda(s))
     got = sim.action_to_torque(cuda(a)).cpu().numpy()
     o = OracleEnv(m, p)
+    nj = sim.nj
     for i in range(n):
         o.set_state(s[i])
-        assert np.abs(o.action_to_torque(a[i]) - got[i]).max() < 3 * TOL_ENV
+        # 1e-6 RELATIVE TO THE OPERANDS of the PD law: tau = clip(kp (q_ref - q) - kd qd): the fp32 terms
+        # kp*q_ref, kp*q and kd*qd are each rounded at their own magnitude before the clip (controllers/PD.py:5-8)
+        if control == "torque":
+            scale = np.ones(nj)
+        else:
+            kp, kd = (a[i, -2], a[i, -1]) if control == "vpd" else (p.kp, p.kd)
+            q_ref = np.clip(a[i, :nj], -1, 1) * 10.0
+            scale = np.maximum(1.0, abs(kp) * (np.abs(q_ref) + np.abs(s[i, 13:13 + nj])) + abs(kd) * np.abs(s[i, 13 + nj:]))
+        assert (np.abs(o.action_to_torque(a[i]) - got[i]) < TOL_ENV * scale).all()
     sim.close()
 
 
@@ -90,7 +100,9 @@ def test_pd_golden_from_reference():
         a = np.clip(z["q_ref"][i] / 10.0, -1, 1)[None]
         got = sim.action_to_torque(cuda(a)).cpu().numpy()[0]
         inside = np.abs(z["q_ref"][i]) <= 10
-        assert np.abs(got[inside] - z["out"][i][inside]).max() < 1e-5   # fp32 inputs: |q|,|qd| up to 60
+        # 1e-6 relative to the operands of the PD law (|q|, |qd| up to 60 in the reference-generated cases)
+        scale = np.maximum(1.0, abs(p.kp) * (np.abs(z["q_ref"][i]) + np.abs(z["q"][i])) + abs(p.kd) * np.abs(z["qd"][i]))
+        assert (np.abs(got - z["out"][i]) < TOL_ENV * scale)[inside].all()
         sim.close()
 
 
@@ -150,14 +162,67 @@ def test_reward_given_identical_state_1e6(task, control):
     obs, rew, done = sim.step(cuda(a))
     rew, done = rew.cpu().numpy(), done.cpu().numpy()
     o = OracleEnv(m, p)
-    tol = 3e-5 if task == "pointgoal" else TOL_ENV   # see tests/test_emu_parity.py: fp32 ulp of x times 60
     for i in range(n):
         o.set_state(s[i])
         if task == "pointgoal":
             o.set_goal(3.0, 0.5)
         _, r, d, _ = o.step(a[i])
         assert d == (done[i] > 0.5)
-        assert abs(r - rew[i]) < tol * max(1.0, abs(r)), (i, r, rew[i])
+        # 1e-6 relative to the operands: the pointgoal progress term is (old potential - new potential) / dt
+        # (baseEnv.py:137), a difference of two distances of ~3 m divided by 1/60 s -- operand magnitude
+        # potential / dt ~ 180; every other term is O(1)
+        scale = max(1.0, abs(r))
+        if task == "pointgoal":
+            scale = max(scale, float(np.hypot(s[i, 0] - 3.0, s[i, 1] - 0.5)) / p.pointgoal_dt)
+        assert abs(r - rew[i]) < TOL_ENV * scale, (i, r, rew[i], scale)
+    sim.close()
+
+
+@pytest.mark.parametrize("robot,task,H", [("solo8", "walk", 1), ("solo12", "pointgoal", 2)])
+def test_observation_with_injected_contact_sets_1e6(robot, task, H):
+    """the contact flag is 1 iff some ground-foot contact point has normal force < 0.2 N
+    (solo.py:310-323 with tuple index 9).  Contact records on both sides of the threshold, at it, at zero force
+    and absent are injected into the GPU handle (solo_set_contacts) and the oracle; the whole observation --
+    flag slots included, in the current block and in the history differences -- is held to 1e-6, and
+    solo_get_contacts column 0 (the flag itself) must be equal."""
+    rng = np.random.default_rng(28)
+    n = 128
+    sim, m, p = make_sim(robot, n, task=task, H=H)
+    s = random_states(rng, n, sim.nj, vel_scale=0.3)
+    if task == "pointgoal":
+        sim.set_goals(cuda(np.tile([1.5, -1.25], (n, 1))))
+    choices = np.array([-1.0, 0.0, 0.05, 0.1999, 0.2, 0.2001, 0.7, 6.0])
+    force = rng.choice(choices, size=(n, 4)).astype(np.float32).astype(np.float64)
+    force[0], force[1], force[2] = -1.0, 0.1, 5.0
+    sim.set_state(cuda(s))                    # clears the record and fills the history with flags = 0
+    sim.set_contacts(cuda(force))
+    got = sim.get_observation().cpu().numpy()
+    con = sim.get_contacts().cpu().numpy()
+    o = OracleEnv(m, p)
+    nflag = 0
+    for i in range(n):
+        if task == "pointgoal":
+            o.set_goal(1.5, -1.25)
+        o.set_state(s[i])
+        o.set_contacts(force[i])
+        ref = o.get_observation()
+        assert (obs_diff(ref, got[i], o.d0) / np.maximum(1.0, np.abs(ref))).max() < TOL_ENV
+        oc = o.get_contacts()
+        assert (oc[:, 0] == con[i, :, 0]).all() and (oc[:, 1] == con[i, :, 1]).all()
+        want = ((force[i] >= 0) & (force[i] < 0.2)).astype(float)
+        assert (con[i, :, 0] == want).all()
+        fl = flag_slots(o.d0, sim.nj, 1)
+        assert (got[i][fl] == want).all()
+        nflag += int(want.sum())
+    assert nflag > n          # both flag values are well represented
+    # a step pushes the injected record into the history (solo.py:262): these are free-flight states, so the
+    # new record is empty (flag 0) and the first difference block carries exactly  0 - injected flag
+    obs, _, _ = sim.step(torch.zeros(n, sim.act_dim, device="cuda"))
+    obs = obs.cpu().numpy()
+    d0 = sim.d0
+    fl = flag_slots(d0, sim.nj, 2)
+    want = ((force >= 0) & (force < 0.2)).astype(np.float32)
+    assert (obs[:, fl[:4]] == 0).all() and (obs[:, fl[4:8]] == -want).all()
     sim.close()
 
 
@@ -165,7 +230,7 @@ def _hold_torque(s, nj, target, kp=3.0, kd=0.05):
     return np.clip(kp * (target - s[:, 13:13 + nj]) - kd * s[:, 13 + nj:], -3, 3)
 
 
-@pytest.mark.parametrize("build", ["latency", "throughput"])
+@pytest.mark.parametrize("build", BUILDS)
 @pytest.mark.parametrize("robot", ROBOTS)
 def test_contact_substep_1e3(robot, build, monkeypatch):
     """Bent-leg stance under a joint PD hold + noise: 3-4 feet in contact.  Identical
@@ -195,10 +260,59 @@ def test_contact_substep_1e3(robot, build, monkeypatch):
             co = o.get_contacts()
             assert (co[:, 1] == con[i, :, 1]).all()
             assert np.abs(co[:, 2] - con[i, :, 2]).max() < 2e-2 * max(1.0, co[:, 2].max())
+            clear = np.abs(co[:, 2] - p.contact_flag_force) > 2e-2      # the flag is a threshold test on the force
+            assert (co[clear, 0] == con[i, clear, 0]).all()
             ncs.append(co[:, 1].sum())
         cur = nxt
     assert np.mean(ncs) > 2.5
     assert max(errs) < TOL_CONTACT, (max(errs), np.median(errs))
+    sim.close()
+
+
+@pytest.mark.parametrize("build", BUILDS)
+def test_contact_substep_exceedance_rate_over_1e5_substeps(build, monkeypatch):
+    """The 1e-3 single-substep bound at scale.  DESIGN.md §5: the PGS leaves the sweep loop on a residual
+    threshold (Bullet's 1e-7); when the fp32 and fp64 iterations cross it a few sweeps apart the two states
+    differ by the remaining convergence error.  >= 1e5 contact substeps from re-injected fp32-representable
+    states (2048 envs x 50 substeps, bent-leg stance under a PD hold + noise), GPU through the C-ABI against
+    the oracle (batched on the host threads).  Budget, asserted: at most 5 in 10^4 contact substeps exceed 1e-3,
+    none exceeds 1e-2, median below 1e-4; the measured rate is printed."""
+    from oracle.oracle import OracleVecEnv
+    monkeypatch.setenv("SOLO_STEP_VARIANT", build)
+    rng = np.random.default_rng(44)
+    n, T = 2048, 50
+    sim, m, p = make_sim("solo12", n)
+    nj = sim.nj
+    ov = OracleVecEnv(m, p, n)
+    cur = stance_states(rng, n, nj)
+    target = cur[:, 13:13 + nj].copy()
+    errs, flag_cmp, flag_bad, sweeps_differ = [], 0, 0, 0
+    for t in range(T):
+        tau = (_hold_torque(cur, nj, target) + rng.normal(size=(n, nj)) * 0.3).astype(np.float32).astype(np.float64)
+        sim.set_state(cuda(cur))
+        sim.substep(cuda(tau))
+        nxt = sim.get_state().cpu().numpy().astype(np.float64)
+        con = sim.get_contacts().cpu().numpy()
+        ref, rcon, _ = ov.substep_from(cur, tau)
+        incontact = rcon[:, :, 1].sum(1) > 0
+        assert (rcon[:, :, 1] == con[:, :, 1]).all()
+        e = (np.abs(ref - nxt) / np.maximum(1.0, np.abs(ref))).max(axis=1)
+        errs.append(e[incontact])
+        clear = np.abs(rcon[:, :, 2] - p.contact_flag_force) > 2e-2
+        flag_cmp += int(clear.sum()); flag_bad += int((rcon[:, :, 0] != con[:, :, 0])[clear].sum())
+        # fallen or flailing envs go back to a fresh stance so that the sample stays a contact sample
+        bad = (nxt[:, 2] < 0.12) | (np.abs(nxt[:, 13 + nj:]).max(1) > 30) | ~np.isfinite(nxt).all(1)
+        if bad.any():
+            nxt[bad] = stance_states(rng, int(bad.sum()), nj)
+        cur = nxt
+    errs = np.concatenate(errs)
+    rate = float((errs > TOL_CONTACT).mean())
+    print(f"[{build}] {len(errs)} contact substeps: median {np.median(errs):.2e} p99 {np.quantile(errs, 0.99):.2e} "
+          f"max {errs.max():.2e}; exceed 1e-3: {rate:.2e}")
+    assert len(errs) >= 100000
+    assert rate <= 5e-4, rate
+    assert errs.max() < 1e-2 and np.median(errs) < 1e-4
+    assert flag_bad == 0, (flag_bad, flag_cmp)
     sim.close()
 
 
@@ -262,7 +376,7 @@ def test_builds_agree_on_a_rollout(monkeypatch):
     from solorl_b200.envs import SoloVecEnv
     cfg = make_config("solo12", task="walk", H=1)
     outs = []
-    for build in ("latency", "throughput"):
+    for build in BUILDS:
         monkeypatch.setenv("SOLO_STEP_VARIANT", build)
         env = SoloVecEnv(cfg, 256, device="cuda:0", seed=4)
         env.reset()
@@ -271,11 +385,12 @@ def test_builds_agree_on_a_rollout(monkeypatch):
         o, r, d, _ = env.step(a)
         outs.append((o.clone(), r.clone(), d.clone()))
         env.close()
-    assert torch.equal(outs[0][2], outs[1][2])
-    assert (outs[0][1] - outs[1][1]).abs().max() < 1e-4
-    df = obs_diff(outs[0][0].cpu().numpy(), outs[1][0].cpu().numpy(), 38)
-    df[:, flag_slots(38, 12, 2)] = 0
-    assert df.max() < 1e-3
+    for other in outs[1:]:
+        assert torch.equal(outs[0][2], other[2])
+        assert (outs[0][1] - other[1]).abs().max() < 1e-4
+        df = obs_diff(outs[0][0].cpu().numpy(), other[0].cpu().numpy(), 38)
+        df[:, flag_slots(38, 12, 2)] = 0
+        assert df.max() < 1e-3
 
 
 def test_step_before_reset_is_an_error():
@@ -653,7 +768,7 @@ def test_episode_length_one_and_curriculum_hook():
     envs.close()
 
 
-@pytest.mark.parametrize("build", ["latency", "throughput"])
+@pytest.mark.parametrize("build", BUILDS)
 @pytest.mark.parametrize("airborne", [False, True])
 @pytest.mark.parametrize("robot", ROBOTS)
 def test_joint_limit_substep_1e3(robot, airborne, build, monkeypatch):
@@ -706,7 +821,7 @@ def test_joint_limits_bound_the_joint_range_at_full_size():
     assert worst[1] < 10.6 and worst[0] > 15.0, worst
 
 
-@pytest.mark.parametrize("build", ["latency", "throughput"])
+@pytest.mark.parametrize("build", BUILDS)
 @pytest.mark.parametrize("n", [1, 37, 264])
 def test_outputs_stay_inside_their_buffers(n, build, monkeypatch):
     """Canaries around every caller-owned output of solo_step / solo_reset / solo_get_* (ragged batches, both
@@ -744,3 +859,81 @@ def test_outputs_stay_inside_their_buffers(n, build, monkeypatch):
         torch.cuda.synchronize()
         assert intact(buf, count) and (buf[pad:pad + count] != canary).all()
     sim.close()
+
+
+# ---- advisor findings of round 1 ----------------------------------------------------------------------------
+def test_curriculum_increment_reaches_a_captured_step_graph():
+    """The goal radius lives in device memory: a step captured into a CUDA graph BEFORE increment_curriculum()
+    samples goals with the NEW radius when replayed afterwards (a by-value kernel parameter stayed at its
+    capture-time value: ADVICE r1)."""
+    from solorl_b200.envs import make_vec_envs
+    cfg = make_config("solo12", task="pointgoal", H=0, episode_length=1)     # every step ends and resamples
+    n = 256
+    envs = make_vec_envs(cfg, n, seed=2)
+    envs.reset()
+    venv = envs.envs.venv
+    a = torch.zeros(n, 12, device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        venv.sim.step(a)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        venv.sim.step(a)
+    r0 = venv.goal_radius
+    for _ in range(3):
+        g.replay()
+    goals = venv.sim.obs[:, -2:] * 2.0
+    assert (goals.abs() <= r0 + 1e-5).all()
+    for _ in range(3):
+        envs.increment_curriculum()                                          # r0 + 3
+    seen = torch.zeros((), device="cuda")
+    for _ in range(6):
+        g.replay()
+        seen = torch.maximum(seen, (venv.sim.obs[:, -2:] * 2.0).abs().max())
+    assert float(seen) > r0 + 0.5 and float(seen) <= r0 + 3.0 + 1e-5
+    envs.close()
+
+
+def test_public_wrapper_hands_out_fresh_tensors_and_frozen_infos():
+    """make_vec_envs(...).step/reset return tensors the next call does not overwrite (the reference builds new
+    ones every step, agents/ppo/envs.py:192-196), and an infos object keeps describing ITS step."""
+    from solorl_b200.envs import make_vec_envs
+    cfg = make_config("solo8", task="walk", H=1, episode_length=3)
+    envs = make_vec_envs(cfg, 16, seed=5)
+    obs0 = envs.reset()
+    keep0 = obs0.clone()
+    a = torch.zeros(16, 8, device="cuda")
+    obs1, r1, d1, i1 = envs.step(a)
+    assert torch.equal(obs0, keep0) and obs1.data_ptr() != obs0.data_ptr()
+    keep1 = (obs1.clone(), r1.clone(), d1.clone())
+    obs2, r2, d2, i2 = envs.step(a)
+    obs3, r3, d3, i3 = envs.step(a)                                           # episode_length 3: everybody times out
+    assert torch.equal(obs1, keep1[0]) and torch.equal(r1, keep1[1]) and torch.equal(d1, keep1[2])
+    assert d3.sum().item() == 16 and d1.sum().item() == 0
+    for _ in range(2):
+        envs.step(a)
+    assert i1[0] == {} and i3[0]["episode_length"] == 3 and i3[5]["timeout"] is True    # inspected two steps later
+    # the zero-copy calls of the in-repo trainers do alias the handle's buffers
+    o_a, _, _, _ = envs.step_inplace(a)
+    o_b, _, _, _ = envs.step_inplace(a)
+    assert o_a.data_ptr() == o_b.data_ptr()
+    envs.close()
+
+
+def test_reset_cache_with_a_settle_span_above_one_warp():
+    """solo_create fills one reset-cache row per settle count; spans above 32 rows used to be left
+    uninitialised.  cached == simulated, bitwise, with 40 settle counts."""
+    from solorl_b200.envs import SoloVecEnv
+    cfg = make_config("solo12", task="walk", H=1, episode_length=6, settle_min=1, settle_max=41)
+    e1 = SoloVecEnv(cfg, 128, device="cuda:0", seed=5)
+    e2 = SoloVecEnv(dict(cfg, reset_mode="simulate"), 128, device="cuda:0", seed=5)
+    assert torch.equal(e1.reset(), e2.reset())
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(14):
+        a = torch.rand(128, 12, device="cuda", generator=g) * 2 - 1
+        o1, r1, d1, _ = e1.step(a)
+        o2, r2, d2, _ = e2.step(a)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    e1.close(); e2.close()
