@@ -8,7 +8,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_PKG, "csrc", "solo_kernels.cu")
-_DEPS = [_SRC] + [os.path.join(_PKG, "csrc", f) for f in ("solo_core.cuh", "solo_env.cuh", "solo_host_model.h")] + [
+_DEPS = [_SRC] + [os.path.join(_PKG, "csrc", f) for f in ("solo_core.cuh", "solo_env.cuh", "solo_host_model.h", "solo_wide.cuh")] + [
     os.path.join(os.path.dirname(_PKG), "include", "solo_b200.h")]
 LIB = os.path.join(_PKG, "libsolo_b200.so")
 _BENCH_SRC = os.path.join(_PKG, "csrc", "bench_util.cu")

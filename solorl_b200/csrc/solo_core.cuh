@@ -354,123 +354,131 @@ SOLO_HD void base_prepare(const BaseState& s, BaseWork& w) {
   mat3T_mulv(w.R, s.v, w.vb);
 }
 
-/* Passes 1+2 of the articulated-body algorithm for one leg (outward kinematics and bias
- * forces, then inward articulated inertia).  Result: the leg's articulated inertia and
- * bias force as seen by the base (IAleg, pAleg), about the base origin, base axes. */
+/* Kinematic state carried down a leg while walking outward from the base: rotation of the current link,
+ * position O_k of its joint origin relative to the base origin, and the spatial velocity (angular, linear
+ * velocity of the point at O_k) of the current link -- all in base axes. */
+struct LegKin {
+  float R[9], o[3], va[3], vl[3];
+};
+SOLO_HD void legkin_init(const BaseWork& bw, LegKin& kn) {
+  const float I3[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+#pragma unroll
+  for (int i = 0; i < 9; i++) kn.R[i] = I3[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { kn.o[i] = 0.f; kn.va[i] = bw.wb[i]; kn.vl[i] = bw.vb[i]; }
+}
+/* Step through joint k (k is a compile-time constant after unrolling at every call site): r = O_k - O_{k-1},
+ * a = joint axis, cJ = velocity-product acceleration v x (a qd, 0); kn ends up describing link k. */
 template <int NJL>
-SOLO_HD void leg_inward(const LegConst& lc, const SimConst& sc, const BaseWork& bw, Lane<NJL>& ln,
-                        const float* tau, Sym6& IAleg, float* pAleg) {
-  float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
-  float o[3] = {0.f, 0.f, 0.f};
-  float va[3] = {bw.wb[0], bw.wb[1], bw.wb[2]};
-  float vl[3] = {bw.vb[0], bw.vb[1], bw.vb[2]};   /* linear velocity of the point at O_k */
-  float pk[NJL][6], com[NJL][3], Ic[NJL][6];
+SOLO_HD void legkin_joint(const LegConst& lc, int k, float q, float qd, LegKin& kn, float* r, float* a, float* cJ) {
+  float* R = kn.R;
+  mat3_mulv(R, lc.jo[k], r);
+  kn.o[0] += r[0]; kn.o[1] += r[1]; kn.o[2] += r[2];
+  cross3_add(kn.va, r, kn.vl);                           /* move the reference point to O_k */
+  constexpr int kAxX = 0;
+  const int ax = axis_of<NJL>(k);
+  a[0] = R[ax]; a[1] = R[3 + ax]; a[2] = R[6 + ax];
+  float sn, cs;
+  solo_sincos(q, &sn, &cs);
+  if (ax == kAxX) { /* R <- R Rx(q): col1' = c col1 + s col2 ; col2' = -s col1 + c col2 */
 #pragma unroll
-  for (int k = 0; k < NJL; k++) {
-    float t[3];
-    float* r = ln.r[k];
-    mat3_mulv(R, lc.jo[k], r);
-    o[0] += r[0]; o[1] += r[1]; o[2] += r[2];
-    cross3_add(va, r, vl);                           /* move the reference point to O_k */
-    constexpr int kAxX = 0;
-    const int ax = axis_of<NJL>(k);
-    float* a = ln.ax[k];
-    a[0] = R[ax]; a[1] = R[3 + ax]; a[2] = R[6 + ax];
-    float sn, cs;
-    solo_sincos(ln.q[k], &sn, &cs);
-    if (ax == kAxX) { /* R <- R Rx(q): col1' = c col1 + s col2 ; col2' = -s col1 + c col2 */
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        float c1 = R[3 * i + 1], c2 = R[3 * i + 2];
-        R[3 * i + 1] = cs * c1 + sn * c2;
-        R[3 * i + 2] = cs * c2 - sn * c1;
-      }
-    } else {          /* R <- R Ry(q): col0' = c col0 - s col2 ; col2' = s col0 + c col2 */
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        float c0 = R[3 * i + 0], c2 = R[3 * i + 2];
-        R[3 * i + 0] = cs * c0 - sn * c2;
-        R[3 * i + 2] = sn * c0 + cs * c2;
-      }
+    for (int i = 0; i < 3; i++) {
+      float c1 = R[3 * i + 1], c2 = R[3 * i + 2];
+      R[3 * i + 1] = cs * c1 + sn * c2;
+      R[3 * i + 2] = cs * c2 - sn * c1;
     }
-    /* joint velocity (a qd, 0) and velocity-product acceleration cJ = v x (a qd, 0) */
-    float qd = ln.qd[k];
-    float wJ[3] = {a[0] * qd, a[1] * qd, a[2] * qd};
-    cross3(va, wJ, ln.cJ[k]);
-    cross3(vl, wJ, ln.cJ[k] + 3);
-    va[0] += wJ[0]; va[1] += wJ[1]; va[2] += wJ[2];
-    /* COM (relative to O_k) and rotated inertia */
-    mat3_mulv(R, lc.c[k], com[k]);
-    {
-      const float* I = lc.I[k];
-      float T[9];
+  } else {          /* R <- R Ry(q): col0' = c col0 - s col2 ; col2' = s col0 + c col2 */
 #pragma unroll
-      for (int i = 0; i < 3; i++) {
-        T[3 * i + 0] = R[3 * i] * I[0] + R[3 * i + 1] * I[1] + R[3 * i + 2] * I[2];
-        T[3 * i + 1] = R[3 * i] * I[1] + R[3 * i + 1] * I[3] + R[3 * i + 2] * I[4];
-        T[3 * i + 2] = R[3 * i] * I[2] + R[3 * i + 1] * I[4] + R[3 * i + 2] * I[5];
-      }
-      Ic[k][0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2];
-      Ic[k][1] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5];
-      Ic[k][2] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8];
-      Ic[k][3] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5];
-      Ic[k][4] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8];
-      Ic[k][5] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8];
+    for (int i = 0; i < 3; i++) {
+      float c0 = R[3 * i + 0], c2 = R[3 * i + 2];
+      R[3 * i + 0] = cs * c0 - sn * c2;
+      R[3 * i + 2] = sn * c0 + cs * c2;
     }
-    /* momentum and velocity-product bias  p = v x* (I v), moments about O_k */
-    float vc[3], l[3], nc[3], nO[3];
-    cross3(va, com[k], vc);
-    vc[0] += vl[0]; vc[1] += vl[1]; vc[2] += vl[2];
-    float m = lc.m[k];
-    l[0] = m * vc[0]; l[1] = m * vc[1]; l[2] = m * vc[2];
-    sym3_mulv(Ic[k], va, nc);
-    cross3(com[k], l, nO);
-    nO[0] += nc[0]; nO[1] += nc[1]; nO[2] += nc[2];
-    cross3(va, nO, pk[k]);
-    cross3_add(vl, l, pk[k]);
-    cross3(va, l, pk[k] + 3);
-    /* Bullet link damping: drag  m v_c (k + k|v_c|)  and  I w (k + k|w|)  per URDF link */
-    float wn = solo_sqrt_approx(dot3(va, va));
-    float sa = sc.kang + sc.kang * wn;
-    if (k < NJL - 1) {
-      float sl = sc.klin + sc.klin * solo_sqrt_approx(dot3(vc, vc));
-      float f[3] = {l[0] * sl, l[1] * sl, l[2] * sl};
-      pk[k][3] += f[0]; pk[k][4] += f[1]; pk[k][5] += f[2];
-      cross3_add(com[k], f, pk[k]);
-      pk[k][0] += nc[0] * sa; pk[k][1] += nc[1] * sa; pk[k][2] += nc[2] * sa;
-    } else {
-      float cb[3], vb2[3], f[3];
-      /* lower leg proper */
-      mat3_mulv(R, lc.c_own, cb);
-      cross3(va, cb, vb2);
-      vb2[0] += vl[0]; vb2[1] += vl[1]; vb2[2] += vl[2];
-      float sl = lc.m_own * (sc.klin + sc.klin * solo_sqrt_approx(dot3(vb2, vb2)));
-      f[0] = vb2[0] * sl; f[1] = vb2[1] * sl; f[2] = vb2[2] * sl;
-      pk[k][3] += f[0]; pk[k][4] += f[1]; pk[k][5] += f[2];
-      cross3_add(cb, f, pk[k]);
-      /* foot */
-      mat3_mulv(R, lc.c_foot, cb);
-      cross3(va, cb, vb2);
-      vb2[0] += vl[0]; vb2[1] += vl[1]; vb2[2] += vl[2];
-      sl = lc.m_foot * (sc.klin + sc.klin * solo_sqrt_approx(dot3(vb2, vb2)));
-      f[0] = vb2[0] * sl; f[1] = vb2[1] * sl; f[2] = vb2[2] * sl;
-      pk[k][3] += f[0]; pk[k][4] += f[1]; pk[k][5] += f[2];
-      cross3_add(cb, f, pk[k]);
-      /* angular: R Idamp R^T w */
-      float wl[3], Iw[3], tw[3];
-      mat3T_mulv(R, va, wl);
-      sym3_mulv(lc.Idamp, wl, Iw);
-      mat3_mulv(R, Iw, tw);
-      pk[k][0] += tw[0] * sa; pk[k][1] += tw[1] * sa; pk[k][2] += tw[2] * sa;
-    }
-    (void)t;
   }
+  /* joint velocity (a qd, 0) and velocity-product acceleration cJ = v x (a qd, 0) */
+  float wJ[3] = {a[0] * qd, a[1] * qd, a[2] * qd};
+  cross3(kn.va, wJ, cJ);
+  cross3(kn.vl, wJ, cJ + 3);
+  kn.va[0] += wJ[0]; kn.va[1] += wJ[1]; kn.va[2] += wJ[2];
+}
+/* Per-link quantities of link k at the kinematic state kn: COM relative to O_k, inertia about the COM in base
+ * axes, and the bias wrench pk = v x* (I v) + Bullet link damping, moments about O_k. */
+template <int NJL>
+SOLO_HD void link_bias(const LegConst& lc, const SimConst& sc, int k, const LegKin& kn, float* com, float* Ic,
+                       float* pk) {
+  const float* R = kn.R;
+  const float* va = kn.va;
+  const float* vl = kn.vl;
+  mat3_mulv(R, lc.c[k], com);
+  {
+    const float* I = lc.I[k];
+    float T[9];
 #pragma unroll
-  for (int i = 0; i < 9; i++) ln.Rl[i] = R[i];
-  ln.ol[0] = o[0]; ln.ol[1] = o[1]; ln.ol[2] = o[2];
-
-  /* inward pass: carry the articulated inertia up the chain, translating it from O_k to
-   * O_{k-1} after each joint */
+    for (int i = 0; i < 3; i++) {
+      T[3 * i + 0] = R[3 * i] * I[0] + R[3 * i + 1] * I[1] + R[3 * i + 2] * I[2];
+      T[3 * i + 1] = R[3 * i] * I[1] + R[3 * i + 1] * I[3] + R[3 * i + 2] * I[4];
+      T[3 * i + 2] = R[3 * i] * I[2] + R[3 * i + 1] * I[4] + R[3 * i + 2] * I[5];
+    }
+    Ic[0] = T[0] * R[0] + T[1] * R[1] + T[2] * R[2];
+    Ic[1] = T[0] * R[3] + T[1] * R[4] + T[2] * R[5];
+    Ic[2] = T[0] * R[6] + T[1] * R[7] + T[2] * R[8];
+    Ic[3] = T[3] * R[3] + T[4] * R[4] + T[5] * R[5];
+    Ic[4] = T[3] * R[6] + T[4] * R[7] + T[5] * R[8];
+    Ic[5] = T[6] * R[6] + T[7] * R[7] + T[8] * R[8];
+  }
+  /* momentum and velocity-product bias  p = v x* (I v), moments about O_k */
+  float vc[3], l[3], nc[3], nO[3];
+  cross3(va, com, vc);
+  vc[0] += vl[0]; vc[1] += vl[1]; vc[2] += vl[2];
+  float m = lc.m[k];
+  l[0] = m * vc[0]; l[1] = m * vc[1]; l[2] = m * vc[2];
+  sym3_mulv(Ic, va, nc);
+  cross3(com, l, nO);
+  nO[0] += nc[0]; nO[1] += nc[1]; nO[2] += nc[2];
+  cross3(va, nO, pk);
+  cross3_add(vl, l, pk);
+  cross3(va, l, pk + 3);
+  /* Bullet link damping: drag  m v_c (k + k|v_c|)  and  I w (k + k|w|)  per URDF link */
+  float wn = solo_sqrt_approx(dot3(va, va));
+  float sa = sc.kang + sc.kang * wn;
+  if (k < NJL - 1) {
+    float sl = sc.klin + sc.klin * solo_sqrt_approx(dot3(vc, vc));
+    float f[3] = {l[0] * sl, l[1] * sl, l[2] * sl};
+    pk[3] += f[0]; pk[4] += f[1]; pk[5] += f[2];
+    cross3_add(com, f, pk);
+    pk[0] += nc[0] * sa; pk[1] += nc[1] * sa; pk[2] += nc[2] * sa;
+  } else {
+    float cb[3], vb2[3], f[3];
+    /* lower leg proper */
+    mat3_mulv(R, lc.c_own, cb);
+    cross3(va, cb, vb2);
+    vb2[0] += vl[0]; vb2[1] += vl[1]; vb2[2] += vl[2];
+    float sl = lc.m_own * (sc.klin + sc.klin * solo_sqrt_approx(dot3(vb2, vb2)));
+    f[0] = vb2[0] * sl; f[1] = vb2[1] * sl; f[2] = vb2[2] * sl;
+    pk[3] += f[0]; pk[4] += f[1]; pk[5] += f[2];
+    cross3_add(cb, f, pk);
+    /* foot */
+    mat3_mulv(R, lc.c_foot, cb);
+    cross3(va, cb, vb2);
+    vb2[0] += vl[0]; vb2[1] += vl[1]; vb2[2] += vl[2];
+    sl = lc.m_foot * (sc.klin + sc.klin * solo_sqrt_approx(dot3(vb2, vb2)));
+    f[0] = vb2[0] * sl; f[1] = vb2[1] * sl; f[2] = vb2[2] * sl;
+    pk[3] += f[0]; pk[4] += f[1]; pk[5] += f[2];
+    cross3_add(cb, f, pk);
+    /* angular: R Idamp R^T w */
+    float wl[3], Iw[3], tw[3];
+    mat3T_mulv(R, va, wl);
+    sym3_mulv(lc.Idamp, wl, Iw);
+    mat3_mulv(R, Iw, tw);
+    pk[0] += tw[0] * sa; pk[1] += tw[1] * sa; pk[2] += tw[2] * sa;
+  }
+}
+/* Inward pass over one leg: carry the articulated inertia up the chain, translating it from O_k to O_{k-1}
+ * after each joint.  In: ln.ax, ln.r, ln.cJ and the per-link com / Ic / pk.  Out: ln.h, ln.invD, ln.u and the
+ * leg's articulated inertia and bias force as seen by the base (about the base origin, base axes). */
+template <int NJL>
+SOLO_HD void leg_recursion(const LegConst& lc, Lane<NJL>& ln, const float* tau, const float (*pk)[6],
+                           const float (*com)[3], const float (*Ic)[6], Sym6& IAleg, float* pAleg) {
   sym6_zero(IAleg);
 #pragma unroll
   for (int i = 0; i < 6; i++) pAleg[i] = 0.f;
@@ -498,6 +506,26 @@ SOLO_HD void leg_inward(const LegConst& lc, const SimConst& sc, const BaseWork& 
     sym6_shift(IAleg, ln.r[k]);
     cross3_add(ln.r[k], pAleg + 3, pAleg);
   }
+}
+
+/* Passes 1+2 of the articulated-body algorithm for one leg (outward kinematics and bias
+ * forces, then inward articulated inertia).  Result: the leg's articulated inertia and
+ * bias force as seen by the base (IAleg, pAleg), about the base origin, base axes. */
+template <int NJL>
+SOLO_HD void leg_inward(const LegConst& lc, const SimConst& sc, const BaseWork& bw, Lane<NJL>& ln,
+                        const float* tau, Sym6& IAleg, float* pAleg) {
+  LegKin kn;
+  legkin_init(bw, kn);
+  float pk[NJL][6], com[NJL][3], Ic[NJL][6];
+#pragma unroll
+  for (int k = 0; k < NJL; k++) {
+    legkin_joint<NJL>(lc, k, ln.q[k], ln.qd[k], kn, ln.r[k], ln.ax[k], ln.cJ[k]);
+    link_bias<NJL>(lc, sc, k, kn, com[k], Ic[k], pk[k]);
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) ln.Rl[i] = kn.R[i];
+  ln.ol[0] = kn.o[0]; ln.ol[1] = kn.o[1]; ln.ol[2] = kn.o[2];
+  leg_recursion<NJL>(lc, ln, tau, pk, com, Ic, IAleg, pAleg);
 }
 
 /* Base rigid body: add to the summed leg inertias / bias, factor, solve a0 = -IA0^-1 pA0. */
@@ -564,11 +592,13 @@ SOLO_HD void base_add_velocity(const SimConst& sc, BaseState& s, const float* dw
   }
 }
 
-/* Contact rows of one foot.  bw must hold the PRE-update rotation (poses do not change
- * between the ABA and the constraint solve) and st the POST-update velocity v*. */
+/* Contact geometry of one foot: distance of the collision sphere to the plane (ln.dist, ln.active), the contact
+ * point relative to O_last (rc) and the spatial velocity of the last link about O_last with the UPDATED
+ * velocities (v6), all in base coordinates.  bw holds the PRE-update rotation (poses do not change between the
+ * ABA and the constraint solve), st the POST-update velocity v*. */
 template <int NJL>
-SOLO_HD void contact_setup(const LegConst& lc, const ModelConst& mc, const SimConst& sc,
-                           const BaseState& st, const BaseWork& bw, Lane<NJL>& ln) {
+SOLO_HD void contact_geometry(const LegConst& lc, const ModelConst& mc, const SimConst& sc, const BaseState& st,
+                              const BaseWork& bw, Lane<NJL>& ln, float* rc, float* v6) {
   float rfl[3];                                             /* sphere centre relative to O_last */
   mat3_mulv(ln.Rl, lc.foot_ctr, rfl);
   const float nb[3] = {bw.R[6], bw.R[7], bw.R[8]};          /* world z in base coordinates */
@@ -576,11 +606,8 @@ SOLO_HD void contact_setup(const LegConst& lc, const ModelConst& mc, const SimCo
   float height = st.p[2] + dot3(nb, rf);
   ln.dist = height - mc.foot_r;
   ln.active = ln.dist < sc.margin;
-  float rc[3] = {rfl[0] - mc.foot_r * nb[0], rfl[1] - mc.foot_r * nb[1], rfl[2] - mc.foot_r * nb[2]};
-  /* btPlaneSpace1((0,0,1)) = (0,-1,0), (1,0,0), expressed in base coordinates */
-  float d[3][3] = {{nb[0], nb[1], nb[2]}, {-bw.R[3], -bw.R[4], -bw.R[5]}, {bw.R[0], bw.R[1], bw.R[2]}};
+  rc[0] = rfl[0] - mc.foot_r * nb[0]; rc[1] = rfl[1] - mc.foot_r * nb[1]; rc[2] = rfl[2] - mc.foot_r * nb[2];
   /* spatial velocity of the last link about O_last with the updated velocities */
-  float v6[6];
   mat3T_mulv(bw.R, st.w, v6);
   mat3T_mulv(bw.R, st.v, v6 + 3);
 #pragma unroll
@@ -588,41 +615,68 @@ SOLO_HD void contact_setup(const LegConst& lc, const ModelConst& mc, const SimCo
     cross3_add(v6, ln.r[k], v6 + 3);
     v6[0] += ln.ax[k][0] * ln.qd[k]; v6[1] += ln.ax[k][1] * ln.qd[k]; v6[2] += ln.ax[k][2] * ln.qd[k];
   }
+}
+/* One contact row (m = 0 normal, 1 / 2 the friction directions of btPlaneSpace1((0,0,1)) = (0,-1,0), (1,0,0)):
+ * unit impulse along direction m at the contact point, propagated up the leg (sPm[k] = S_k . wrench at joint k)
+ * to the base (P), K = IA0^-1 P, and the target relative velocity b. */
+template <int NJL>
+SOLO_HD void contact_row(const SimConst& sc, const float* R, const Ldl6& F, const float (*ax)[3],
+                         const float (*r)[3], const float (*h)[6], const float* invD, const float* rc,
+                         const float* v6, float dist, int m, float* sPm, float* P, float* K, float& b) {
+  float d[3];
+  if (m == 0) { d[0] = R[6]; d[1] = R[7]; d[2] = R[8]; }
+  else if (m == 1) { d[0] = -R[3]; d[1] = -R[4]; d[2] = -R[5]; }
+  else { d[0] = R[0]; d[1] = R[1]; d[2] = R[2]; }
+  float w[6];
+  cross3(rc, d, w);
+  w[3] = d[0]; w[4] = d[1]; w[5] = d[2];
+  float vel = dot6(w, v6);
+#pragma unroll
+  for (int k = NJL - 1; k >= 0; k--) {
+    float s = dot3(ax[k], w);
+    sPm[k] = s;
+    float g = s * invD[k];
+#pragma unroll
+    for (int i = 0; i < 6; i++) w[i] -= h[k][i] * g;
+    cross3_add(r[k], w + 3, w);                        /* moments about the parent's origin */
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) { P[i] = w[i]; K[i] = w[i]; }
+  ldl6_solve(F, K);
+  if (m == 0) {
+    float pen = dist + sc.slop;
+    /* speculative contact while separated, ERP push-out while penetrating */
+    b = -vel - pen * (pen > 0.f ? sc.inv_dt : sc.erp * sc.inv_dt);
+  } else {
+    b = -vel;
+  }
+}
+/* leg-local block L = sum_k sP_k sP_k^T invD_k  (xx xy xz yy yz zz over m,n) */
+template <int NJL>
+SOLO_HD void contact_local_block(Lane<NJL>& ln) {
 #pragma unroll
   for (int i = 0; i < 6; i++) ln.Lm[i] = 0.f;
-#pragma unroll
-  for (int m = 0; m < 3; m++) {
-    float w[6];
-    cross3(rc, d[m], w);
-    w[3] = d[m][0]; w[4] = d[m][1]; w[5] = d[m][2];
-    float vel = dot6(w, v6);
-#pragma unroll
-    for (int k = NJL - 1; k >= 0; k--) {
-      float s = dot3(ln.ax[k], w);
-      ln.sP[k][m] = s;
-      float g = s * ln.invD[k];
-#pragma unroll
-      for (int i = 0; i < 6; i++) w[i] -= ln.h[k][i] * g;
-      cross3_add(ln.r[k], w + 3, w);                        /* moments about the parent's origin */
-    }
-#pragma unroll
-    for (int i = 0; i < 6; i++) { ln.P[m][i] = w[i]; ln.K[m][i] = w[i]; }
-    ldl6_solve(bw.F, ln.K[m]);
-    if (m == 0) {
-      float pen = ln.dist + sc.slop;
-      /* speculative contact while separated, ERP push-out while penetrating */
-      ln.b[0] = -vel - pen * (pen > 0.f ? sc.inv_dt : sc.erp * sc.inv_dt);
-    } else {
-      ln.b[m] = -vel;
-    }
-  }
-  /* leg-local block L = sum_k sP_k sP_k^T invD_k  (xx xy xz yy yz zz over m,n) */
 #pragma unroll
   for (int k = 0; k < NJL; k++) {
     float g0 = ln.sP[k][0] * ln.invD[k], g1 = ln.sP[k][1] * ln.invD[k], g2 = ln.sP[k][2] * ln.invD[k];
     ln.Lm[0] += g0 * ln.sP[k][0]; ln.Lm[1] += g0 * ln.sP[k][1]; ln.Lm[2] += g0 * ln.sP[k][2];
     ln.Lm[3] += g1 * ln.sP[k][1]; ln.Lm[4] += g1 * ln.sP[k][2]; ln.Lm[5] += g2 * ln.sP[k][2];
   }
+}
+/* Contact rows of one foot (the three functions above, one lane doing all of it). */
+template <int NJL>
+SOLO_HD void contact_setup(const LegConst& lc, const ModelConst& mc, const SimConst& sc,
+                           const BaseState& st, const BaseWork& bw, Lane<NJL>& ln) {
+  float rc[3], v6[6];
+  contact_geometry<NJL>(lc, mc, sc, st, bw, ln, rc, v6);
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    float sPm[NJL];
+    contact_row<NJL>(sc, bw.R, bw.F, ln.ax, ln.r, ln.h, ln.invD, rc, v6, ln.dist, m, sPm, ln.P[m], ln.K[m], ln.b[m]);
+#pragma unroll
+    for (int k = 0; k < NJL; k++) ln.sP[k][m] = sPm[k];
+  }
+  contact_local_block<NJL>(ln);
 }
 
 /* ------------------------------------------------------------------ joint-limit rows

@@ -18,7 +18,7 @@
  *   q,qd  [NJL][cap][4] : joint k of leg l of env e at ((k*cap+e)*4+l)  (one float4 per env and k,
  *                      consecutive threads read consecutive words)
  *   cforce[cap][4]   : normal force of the last substep per foot, <0 = no contact point
- *   hist  [H][cap][D0], book [cap] (EnvBook), stats [cap] (SoloEpisodeStats)
+ *   hist  [H][cap][D0], currow [cap][D0], book [cap] (EnvBook), stats [cap] (SoloEpisodeStats)
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -35,9 +35,10 @@
 
 namespace solo {
 
-constexpr int kBlockThreads = 32;   /* one warp per block */
+constexpr int kBlockThreads = 32;   /* threads per env warp: eight envs x four legs */
 
 enum { MODE_STEP = 0, MODE_SETTLE = 1, MODE_SUBSTEP = 2 };
+enum { VARIANT_LATENCY = 0, VARIANT_THROUGHPUT = 1, VARIANT_WIDE = 2 };
 
 struct DevArrays {
   float* base;
@@ -45,6 +46,7 @@ struct DevArrays {
   float* qd;
   float* cforce;
   float* hist;
+  float* currow;     /* [cap][D0] get_current_state() of the env as it stands (the row the next step pushes into the history) */
   EnvBook* book;
   SoloEpisodeStats* stats;
   /* reset cache: one row per settle count (settle_min + row) */
@@ -169,6 +171,13 @@ __device__ __forceinline__ float* hist_row(const DevArrays& d, int D0, int h, in
   return d.hist + ((size_t)h * d.cap + e) * D0;
 }
 
+/* get_current_state() of every env is kept as a row of its own (currow), refreshed wherever the state changes
+ * (step / settle / substep epilogue, reset, set_state, set_contacts, set_goals).  The history push at the start of
+ * a step (solo.py:262) then copies that row instead of re-deriving it: the observation arithmetic (Euler angles
+ * from the quaternion, ...) is ~600 SASS instructions per inlined copy, and the step is bound by instruction
+ * fetch (profiles/r2_icache_probe.txt). */
+__device__ __forceinline__ float* cur_row(const DevArrays& d, int D0, int e) { return d.currow + (size_t)e * D0; }
+
 /* deque(maxlen=H).append(get_current_state()) (solo.py:262) */
 template <int NJL>
 __device__ __forceinline__ void push_history(const DevArrays& d, const SimConst& sc, int D0, int e, int leg,
@@ -254,6 +263,7 @@ __device__ __forceinline__ void begin_reset(const DevArrays& d, const SimConst& 
     RowPieces<NJL> cur;
     make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
     for (int h = 0; h < sc.H; h++) store_pieces<NJL>(hist_row(d, D0, h, e), leg, sc.task, cur); /* solo.py:170-171 */
+    store_pieces<NJL>(cur_row(d, D0, e), leg, sc.task, cur);
     bk.settle_left = k;
   } else {
     const int row = k - sc.settle_min;
@@ -292,7 +302,9 @@ __device__ __forceinline__ void pgs_sweeps(PgsLane& pl, const SimConst& sc, int 
     float res_own = 0.f;             /* largest |velocity residual| among the rows this lane relaxed */
     sweep_feet += conv ? 0 : nc;
 #pragma unroll
-    for (int f = 0; f < 4; f++) {   /* feet without contact hold zero rows: no skip branches */
+    for (int f = 0; f < 4; f++) {   /* feet without contact hold zero rows: no skip branches (measured: warp-uniform
+                                     * skips of the rows no still-iterating env holds cost more than they save:
+                                     * 105.6 vs 90.1 us per step at 4096 envs, profiles/r2_experiments.txt) */
       float nv, d, rv;
       pgs_normal_candidate(pl, nv, d, rv);
       const float db = __shfl_sync(kFull, d, gbase + f);
@@ -393,49 +405,39 @@ __device__ __forceinline__ void pgs_sweeps4(PgsLane4& pl, const SimConst& sc, in
   }
 }
 
-/* One Bullet-equivalent substep for the four lanes of an env (see solo_core.cuh).
- * Control flow is kept WARP-uniform (skip masks and the sweep-loop exit are warp votes, envs that
- * have nothing to do contribute exact zeros) so that every shuffle is a full-mask shuffle of a
- * converged warp: group-masked shuffles cost a WARPSYNC each and let the 4-lane groups drift apart. */
-template <int NJL>
-__device__ __forceinline__ void group_substep(const LegConst& lc, const ModelConst& mc, const SimConst& sc,
-                                              int leg, BaseState& st, Lane<NJL>& ln, const float* tau, float& cforce,
-                                              int& nc_sum, int& sweep_feet) {
+/* SOLO_TRACE builds (tools only): cycle stamps inside the substeps of the narrow builds, lane 0 of every block */
+#ifdef SOLO_TRACE
+__device__ long long g_narrow_trace[1024][8][8];
+__device__ int g_trace_substep;
+#define NSTAMP(i) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_narrow_trace[blockIdx.x][g_trace_sub & 7][i] = clock64(); } while (0)
+#else
+#define NSTAMP(i) do { } while (0)
+#endif
+
+/* Second half of a substep for the four lanes of an env: contact / joint-limit rows -> Delassus rows ->
+ * projected Gauss-Seidel -> impulses -> position update.  In: ln (P, K, sP, Lm, b, dist, active of the own
+ * foot and the ABA by-products r, ax, h, invD), bw (pre-update rotation, LDL factor), the limit-row selection. */
+template <int NJL, bool LIMITS>
+__device__ __forceinline__ void contact_solve(const SimConst& sc, int leg, BaseState& st, const BaseWork& bw,
+                                              Lane<NJL>& ln, bool lim_any, int kL, float dirL, float penL,
+                                              float& cforce, int& nc_sum, int& sweep_feet, int g_trace_sub = 0) {
   const unsigned kFull = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned gbase = lane & ~3u;
-  BaseWork bw;
-  base_prepare(st, bw);
-  Sym6 IA;
-  float pA[6], a0[6];
-  leg_inward<NJL>(lc, sc, bw, ln, tau, IA, pA);
-  sum4_sym6(IA);
-#pragma unroll
-  for (int i = 0; i < 6; i++) pA[i] = sum4(pA[i]);
-  base_solve(mc, sc, bw, IA, pA, a0);
-  {
-    float qdd[NJL], aw[3], al[3];
-    leg_outward<NJL>(ln, a0, qdd);
-    base_world_acc(sc, bw, a0, aw, al);
-    base_add_velocity(sc, st, aw, al, sc.dt);
-#pragma unroll
-    for (int k = 0; k < NJL; k++) ln.qd[k] = clampf(ln.qd[k] + sc.dt * qdd[k], -sc.vmax, sc.vmax);
-  }
-  contact_setup<NJL>(lc, mc, sc, st, bw, ln);
   const unsigned ball = __ballot_sync(kFull, ln.active != 0);
   const unsigned amask = (ball >> gbase) & 0xFu;                 /* feet in contact of this env */
   const unsigned wmask = (ball | (ball >> 4) | (ball >> 8) | (ball >> 12) | (ball >> 16) | (ball >> 20) |
                           (ball >> 24) | (ball >> 28)) & 0xFu;     /* ... of any env of the warp */
-  /* joint-limit rows (positions of the start of the substep, velocities after the unconstrained update) */
-  int kL;
-  float dirL, penL;
-  const bool lim_any = limit_select<NJL>(sc, ln, kL, dirL, penL);
   const unsigned lball = __ballot_sync(kFull, lim_any);
   const unsigned lmask = (lball >> gbase) & 0xFu;
   const unsigned lwarp = (lball | (lball >> 4) | (lball >> 8) | (lball >> 12) | (lball >> 16) | (lball >> 20) |
                           (lball >> 24) | (lball >> 28)) & 0xFu;
   float lam3[3] = {0.f, 0.f, 0.f};
-  if (lwarp) {   /* warp-uniform: some env of the warp holds a joint-limit row -> four rows per lane */
+  /* LIMITS (joint_limits on, the reference behaviour): every warp with a contact or a limit row takes the
+   * four-row path, so that one env step executes ONE solve path -- the step is bound by instruction fetch
+   * (profiles/r2_icache_probe.txt), and a block whose warps split over the three-row and the four-row code
+   * streams both through the instruction caches every substep */
+  if (LIMITS ? (lwarp | wmask) != 0 : false) {   /* warp-uniform */
     LimitRow<NJL> lr;
     limit_setup<NJL>(sc, bw, ln, lim_any, kL, dirL, penL, lr);
     PgsLane4 pl;
@@ -459,8 +461,10 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
     const int nc = __popc(amask);
     nc_sum += nc;
     float lam4[4];
+    NSTAMP(3);
     if (sc.cone) pgs_sweeps4<true>(pl, sc, leg, gbase, amask, lmask, lwarp, nc, lam4, sweep_feet);
     else pgs_sweeps4<false>(pl, sc, leg, gbase, amask, lmask, lwarp, nc, lam4, sweep_feet);
+    NSTAMP(4);
     lam3[0] = lam4[0]; lam3[1] = lam4[1]; lam3[2] = lam4[2];
     float part[6], dv0[6];
     impulse_base_part4<NJL>(ln, lr, lam4, part);
@@ -471,7 +475,7 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
     mat3_mulv(bw.R, dv0, dw);
     mat3_mulv(bw.R, dv0 + 3, dvl);
     base_add_velocity(sc, st, dw, dvl, 1.0f);
-  } else if (wmask) {   /* warp-uniform */
+  } else if (!LIMITS && wmask) {   /* warp-uniform */
     PgsLane pl;
     {
       float rows[3][kRows];
@@ -507,99 +511,130 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
   for (int k = 0; k < NJL; k++) ln.q[k] += sc.dt * ln.qd[k];
 }
 
-/* Two builds of the step kernel, chosen per handle from the batch size (choose_variant):
- *   latency    WPB = 4 warps per block, 254 registers (8 warps per SM): shortest per-warp dependent
- *              chain; best while the batch is a single resident wave (<= 8k envs);
- *   throughput WPB = 8, capped at 128 registers (16 warps per SM, 320 B of spills): +30 % once
- *              several waves are resident.
- * WPB > 1 with a block barrier per substep keeps the warps of an SM on the same instruction lines:
- * the substep body is ~54 KB of straight-line SASS against a 32 KB L1.5 instruction cache, so every
- * substep streams its code from L2, and warps that drift apart each pay for the fetch
- * (profiles/r1_sweep_wpb.txt: +6 % at 4096 envs, +38 % at 64k envs against one warp per block).
- * Eight envs per warp always: narrower warps were measured slower at every size
- * (profiles/r1_sweep_epw.txt). */
-template <int NJL, int MINB, int WPB>
-__global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const __grid_constant__ StepArgs args) {
-  __shared__ Smem sm;
-  __shared__ __align__(16) float stage[WPB][8][kStageD];
-  const int tid = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;      /* warp in block */
-  const SimConst& sc = args.sc;
+/* One Bullet-equivalent substep for the four lanes of an env (see solo_core.cuh).
+ * Control flow is kept WARP-uniform (skip masks and the sweep-loop exit are warp votes, envs that
+ * have nothing to do contribute exact zeros) so that every shuffle is a full-mask shuffle of a
+ * converged warp: group-masked shuffles cost a WARPSYNC each and let the 4-lane groups drift apart. */
+template <int NJL, bool LIMITS>
+__device__ __forceinline__ void group_substep(const LegConst& lc, const ModelConst& mc, const SimConst& sc,
+                                              int leg, BaseState& st, Lane<NJL>& ln, const float* tau, float& cforce,
+                                              int& nc_sum, int& sweep_feet, int g_trace_sub = 0) {
+  NSTAMP(0);
+  BaseWork bw;
+  base_prepare(st, bw);
+  Sym6 IA;
+  float pA[6], a0[6];
+  leg_inward<NJL>(lc, sc, bw, ln, tau, IA, pA);
+  sum4_sym6(IA);
+#pragma unroll
+  for (int i = 0; i < 6; i++) pA[i] = sum4(pA[i]);
+  base_solve(mc, sc, bw, IA, pA, a0);
   {
-    const float* src = reinterpret_cast<const float*>(&args.mc.leg[0]);
-    float* dst = reinterpret_cast<float*>(&sm.leg[0]);
-    for (int i = threadIdx.x; i < (int)(sizeof(LegConst) * 4 / sizeof(float)); i += kBlockThreads * WPB) dst[i] = src[i];
+    float qdd[NJL], aw[3], al[3];
+    leg_outward<NJL>(ln, a0, qdd);
+    base_world_acc(sc, bw, a0, aw, al);
+    base_add_velocity(sc, st, aw, al, sc.dt);
+#pragma unroll
+    for (int k = 0; k < NJL; k++) ln.qd[k] = clampf(ln.qd[k] + sc.dt * qdd[k], -sc.vmax, sc.vmax);
   }
-  __syncthreads();
-  const int nsub = (args.mode == MODE_SUBSTEP) ? 1 : sc.frame_skip;
+  NSTAMP(1);
+  contact_setup<NJL>(lc, mc, sc, st, bw, ln);
+  NSTAMP(2);
+  /* joint-limit rows (positions of the start of the substep, velocities after the unconstrained update) */
+  int kL;
+  float dirL, penL;
+  const bool lim_any = LIMITS && limit_select<NJL>(sc, ln, kL, dirL, penL);
+  contact_solve<NJL, LIMITS>(sc, leg, st, bw, ln, lim_any, kL, dirL, penL, cforce, nc_sum, sweep_feet, g_trace_sub);
+  NSTAMP(5);
+}
 
-  const DevArrays& d = args.d;
-  const int el = tid >> 2, leg = tid & 3;
-  const int env = (blockIdx.x * WPB + wib) * 8 + el;
-  const bool valid = env < args.n;
-  const int e = valid ? env : args.n - 1;
-  const long long gid = args.env_id_offset + e;
-  const int D0 = args.D0;
-
+/* Everything an (env, leg) lane carries in registers through one env step. */
+template <int NJL>
+struct EnvLane {
   BaseState st;
   float goal[2], potential;
-  load_base(d.base, e, st, goal, potential);
   Lane<NJL> ln;
+  float cforce;
+  EnvBook bk;
+  float tau[NJL], act[NJL];
+  int e, el, leg, tid;
+  long long gid;
+  bool valid, active;
+};
+typedef float StageTile[8][kStageD];
+
+/* Step prologue of one lane: state load, apply_action (solo.py:224-259), history push (solo.py:262).
+ * wslot = index of this lane's warp among the env warps of the grid (eight envs per warp). */
+template <int NJL>
+__device__ __forceinline__ void step_load(const StepArgs& args, int wslot, int tid, StageTile& stage, EnvLane<NJL>& L) {
+  const SimConst& sc = args.sc;
+  const DevArrays& d = args.d;
+  L.tid = tid;
+  L.el = tid >> 2; L.leg = tid & 3;
+  const int env = wslot * 8 + L.el;
+  L.valid = env < args.n;
+  L.e = L.valid ? env : args.n - 1;
+  L.gid = args.env_id_offset + L.e;
+  const int e = L.e, leg = L.leg;
+  load_base(d.base, e, L.st, L.goal, L.potential);
 #pragma unroll
   for (int k = 0; k < NJL; k++) {
-    ln.q[k] = d.q[((size_t)k * d.cap + e) * 4 + leg];
-    ln.qd[k] = d.qd[((size_t)k * d.cap + e) * 4 + leg];
+    L.ln.q[k] = d.q[((size_t)k * d.cap + e) * 4 + leg];
+    L.ln.qd[k] = d.qd[((size_t)k * d.cap + e) * 4 + leg];
   }
-  float cforce = d.cforce[e * 4 + leg];
-  EnvBook bk = d.book[e];
-  const bool active = valid && (args.mode != MODE_SETTLE || bk.settle_left > 0);
-
-  float tau[NJL], act[NJL];
+  L.cforce = d.cforce[e * 4 + leg];
+  L.bk = d.book[e];
+  L.active = L.valid && (args.mode != MODE_SETTLE || L.bk.settle_left > 0);
 #pragma unroll
-  for (int k = 0; k < NJL; k++) { tau[k] = 0.f; act[k] = 0.f; }
+  for (int k = 0; k < NJL; k++) { L.tau[k] = 0.f; L.act[k] = 0.f; }
   if (args.mode == MODE_STEP) {                     /* apply_action (solo.py:224-259) */
     /* the warp's 8 x A action words arrive as whole lines through the (still unused) observation stage:
      * the actions may live in host-mapped memory (solo_step_host), where scattered 4-byte reads would each
      * be a PCIe round trip */
-    const int e0w = (blockIdx.x * WPB + wib) * 8;
+    const int e0w = wslot * 8;
     const bool tile_ok = (e0w + 8 <= args.n);       /* warp-uniform; ragged / idle warps read directly */
     const float* a = args.in + (size_t)e * args.A;
     if (tile_ok) {
-      float* tile = &stage[wib][0][0];
+      float* tile = &stage[0][0];
       const float* src = args.in + (size_t)e0w * args.A;
       for (int j = tid; j < 8 * args.A; j += 32) tile[j] = src[j];
       __syncwarp();
-      a = tile + el * args.A;
+      a = tile + L.el * args.A;
     }
     float kp = sc.kp, kd = sc.kd;
     if (sc.control == 2) { kp = a[4 * NJL]; kd = a[4 * NJL + 1]; }
 #pragma unroll
     for (int k = 0; k < NJL; k++) {
-      act[k] = a[leg * NJL + k];
-      tau[k] = action_to_torque(sc, act[k], ln.q[k], ln.qd[k], kp, kd);
+      L.act[k] = a[leg * NJL + k];
+      L.tau[k] = action_to_torque(sc, L.act[k], L.ln.q[k], L.ln.qd[k], kp, kd);
     }
     __syncwarp();                                   /* the stage is reused for the observation rows */
   } else if (args.mode == MODE_SUBSTEP) {
 #pragma unroll
-    for (int k = 0; k < NJL; k++) tau[k] = args.in[(size_t)e * 4 * NJL + leg * NJL + k];
+    for (int k = 0; k < NJL; k++) L.tau[k] = args.in[(size_t)e * 4 * NJL + leg * NJL + k];
   }
-
-  if (args.mode != MODE_SUBSTEP && active) {        /* simulator_step: history push (solo.py:262) */
+  if (args.mode != MODE_SUBSTEP && L.active && sc.H > 0) {   /* simulator_step: history push (solo.py:262) */
     RowPieces<NJL> cur;
-    make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
-    push_history<NJL>(d, sc, D0, e, leg, cur);
+    load_pieces<NJL>(cur_row(d, args.D0, e), leg, sc.task, cur);
+    push_history<NJL>(d, sc, args.D0, e, leg, cur);
   }
+  L.bk.nc_sum = 0; L.bk.sweep_feet = 0;
+}
 
-  bk.nc_sum = 0; bk.sweep_feet = 0;
-  for (int s = 0; s < nsub; s++) {                  /* frame_skip x p.stepSimulation() (solo.py:264-265) */
-    if (WPB > 1) __syncthreads();   /* keep the warps of a block on the same instruction lines */
-    const bool torque_on = (s == 0) || sc.torque_hold; /* SURVEY F4 */
-    float tau_s[NJL];
-#pragma unroll
-    for (int k = 0; k < NJL; k++) tau_s[k] = torque_on ? tau[k] : 0.f;
-    group_substep<NJL>(sm.leg[leg], args.mc, sc, leg, st, ln, tau_s, cforce, bk.nc_sum, bk.sweep_feet);
-  }
-
+/* Step epilogue of one lane: pointgoal bookkeeping (solo.py:267-272), observation, reward / termination
+ * (baseEnv.py:47-68), episode record, worker auto-reset (agents/ppo/envs.py:38-40), state store. */
+template <int NJL>
+__device__ __forceinline__ void step_finish(const StepArgs& args, int wslot, StageTile& stage, EnvLane<NJL>& L) {
+  const SimConst& sc = args.sc;
+  const DevArrays& d = args.d;
+  const int e = L.e, leg = L.leg, el = L.el, tid = L.tid, D0 = args.D0;
+  const bool valid = L.valid;
+  BaseState& st = L.st;
+  Lane<NJL>& ln = L.ln;
+  EnvBook& bk = L.bk;
+  float* goal = L.goal;
+  float& potential = L.potential;
+  float& cforce = L.cforce;
   float progress = 0.f;
   if (args.mode != MODE_SUBSTEP && sc.task == 2) {  /* pointgoal bookkeeping (solo.py:267-272) */
     const float oldp = potential;
@@ -608,23 +643,18 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
     if (potential < sc.goal_reach) {
       bk.goals += 1;
       uint32_t w[4];
-      env_rng(args.seed_lo, args.seed_hi, gid, bk, w);
+      env_rng(args.seed_lo, args.seed_hi, L.gid, bk, w);
       sample_goal(w, d.mut[kMutGoalRadius], goal);
     }
   }
 
   if (args.mode == MODE_STEP) {
     bk.timestep += 1;                               /* baseEnv.py:47 */
-    RowPieces<NJL> cur;
-    make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
-    const bool staged = args.D <= kStageD;           /* uniform */
-    float* const row = staged ? &stage[wib][el][0] : args.obs + (size_t)e * args.D;
-    if (valid) write_obs_row<NJL>(d, sc, D0, e, leg, cur, row);
     float sq = 0.f, sa = 0.f;
 #pragma unroll
     for (int k = 0; k < NJL; k++) {
       sq += (sc.task == 0) ? fabsf(ln.q[k]) : ln.q[k] * ln.q[k];
-      sa += act[k] * act[k];
+      sa += L.act[k] * L.act[k];
     }
     /* non-finite-state guard: 0 * x is NaN exactly when x is NaN or Inf */
     float chk = st.p[0] + st.p[1] + st.p[2] + st.q[0] + st.q[1] + st.q[2] + st.q[3] + st.v[0] + st.v[1] + st.v[2] +
@@ -649,42 +679,49 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
         s.nan = bad_state ? 1 : 0;
         d.stats[e] = s;
       }
-      /* worker auto-reset (agents/ppo/envs.py:38-40) */
-      if (valid) {
-        begin_reset<NJL>(d, sc, D0, e, leg, gid, args.seed_lo, args.seed_hi, d.mut[kMutGoalRadius],
+      /* worker auto-reset (agents/ppo/envs.py:38-40): the terminal observation is never returned
+       * (baseEnv.py:54), the reset one is.  Simulate mode: the settle launches that follow rewrite the row. */
+      if (valid)
+        begin_reset<NJL>(d, sc, D0, e, leg, L.gid, args.seed_lo, args.seed_hi, d.mut[kMutGoalRadius],
                          args.reset_simulate, -1, st, ln, cforce, goal, potential, bk);
-        if (!args.reset_simulate) {
-          make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
-          write_obs_row<NJL>(d, sc, D0, e, leg, cur, row);
-        }
-      }
+    }
+    /* ONE derivation of get_current_state per step, after the reset decision: it is the observation's first
+     * block, and the row the next step pushes into the history */
+    RowPieces<NJL> cur;
+    make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
+    const bool staged = args.D <= kStageD;           /* uniform */
+    float* const row = staged ? &stage[el][0] : args.obs + (size_t)e * args.D;
+    if (valid) {
+      write_obs_row<NJL>(d, sc, D0, e, leg, cur, row);
+      store_pieces<NJL>(cur_row(d, D0, e), leg, sc.task, cur);
     }
     if (staged) {                                     /* the warp's 8 x D floats leave as whole lines */
       __syncwarp();
-      const int e0 = (blockIdx.x * WPB + wib) * 8;
+      const int e0 = wslot * 8;
       const int nv = min(8, args.n - e0);
       if ((args.D & 3) == 0) {
         const int d4 = args.D >> 2;
         for (int r = 0; r < nv; r++) {
           float4* dst = reinterpret_cast<float4*>(args.obs + (size_t)(e0 + r) * args.D);
-          const float4* src = reinterpret_cast<const float4*>(&stage[wib][r][0]);
+          const float4* src = reinterpret_cast<const float4*>(&stage[r][0]);
           for (int j = tid; j < d4; j += 32) dst[j] = src[j];
         }
       } else {
         for (int r = 0; r < nv; r++)
-          for (int j = tid; j < args.D; j += 32) args.obs[(size_t)(e0 + r) * args.D + j] = stage[wib][r][j];
+          for (int j = tid; j < args.D; j += 32) args.obs[(size_t)(e0 + r) * args.D + j] = stage[r][j];
       }
     }
-  } else if (args.mode == MODE_SETTLE && active) {
-    bk.settle_left -= 1;
-    if (bk.settle_left == 0 && args.obs != nullptr) {
-      RowPieces<NJL> cur;
-      make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
-      write_obs<NJL>(d, sc, D0, args.D, e, leg, cur, args.obs);
+  } else if (L.active) {                              /* settle step of a simulated reset, or the substep hook */
+    RowPieces<NJL> cur;
+    make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
+    store_pieces<NJL>(cur_row(d, D0, e), leg, sc.task, cur);
+    if (args.mode == MODE_SETTLE) {
+      bk.settle_left -= 1;
+      if (bk.settle_left == 0 && args.obs != nullptr) write_obs<NJL>(d, sc, D0, args.D, e, leg, cur, args.obs);
     }
   }
 
-  if (active) {
+  if (L.active) {
     if (leg == 0) { store_base(d.base, e, st, goal, potential); d.book[e] = bk; }
 #pragma unroll
     for (int k = 0; k < NJL; k++) {
@@ -692,6 +729,89 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
       d.qd[((size_t)k * d.cap + e) * 4 + leg] = ln.qd[k];
     }
     d.cforce[e * 4 + leg] = cforce;
+  }
+}
+
+/* Builds of the step kernel, chosen per handle from the batch size (choose_variant):
+ *   latency    WPB = 4 warps per block, 254 registers (8 warps per SM): shortest per-warp dependent
+ *              chain; best while the batch is a single resident wave (<= 8k envs);
+ *   throughput WPB = 8, capped at 128 registers (16 warps per SM, 320 B of spills): +30 % once
+ *              several waves are resident.
+ * WPB > 1 with a block barrier per substep keeps the warps of an SM on the same instruction lines:
+ * the substep body is ~54 KB of straight-line SASS against a 32 KB L1.5 instruction cache, so every
+ * substep streams its code from L2, and warps that drift apart each pay for the fetch
+ * (profiles/r1_sweep_wpb.txt: +6 % at 4096 envs, +38 % at 64k envs against one warp per block).
+ * Eight envs per warp always: narrower warps were measured slower at every size
+ * (profiles/r1_sweep_epw.txt). */
+template <int NJL, int MINB, int WPB, bool LIMITS>
+__global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const __grid_constant__ StepArgs args) {
+  __shared__ Smem sm;
+  __shared__ __align__(16) StageTile stage[WPB];
+  if (blockIdx.x * (8 * WPB) >= args.n) return;   /* padding blocks of an experiment grid (SOLO_GRID_MIN) */
+  const int tid = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;      /* warp in block */
+  const SimConst& sc = args.sc;
+  {
+    const float* src = reinterpret_cast<const float*>(&args.mc.leg[0]);
+    float* dst = reinterpret_cast<float*>(&sm.leg[0]);
+    for (int i = threadIdx.x; i < (int)(sizeof(LegConst) * 4 / sizeof(float)); i += kBlockThreads * WPB) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int nsub = (args.mode == MODE_SUBSTEP) ? 1 : sc.frame_skip;
+  const int wslot = blockIdx.x * WPB + wib;
+  EnvLane<NJL> L;
+  step_load<NJL>(args, wslot, tid, stage[wib], L);
+  for (int s = 0; s < nsub; s++) {                  /* frame_skip x p.stepSimulation() (solo.py:264-265) */
+    if (WPB > 1) __syncthreads();   /* keep the warps of a block on the same instruction lines */
+    const bool torque_on = (s == 0) || sc.torque_hold; /* SURVEY F4 */
+    float tau_s[NJL];
+#pragma unroll
+    for (int k = 0; k < NJL; k++) tau_s[k] = torque_on ? L.tau[k] : 0.f;
+    group_substep<NJL, LIMITS>(sm.leg[L.leg], args.mc, sc, L.leg, L.st, L.ln, tau_s, L.cforce, L.bk.nc_sum, L.bk.sweep_feet, s);
+  }
+  step_finish<NJL>(args, wslot, stage[wib], L);
+}
+
+}  // namespace solo
+#include "solo_wide.cuh"
+namespace solo {
+
+/* The wide build (solo_wide.cuh): warpgroup 0 runs the env step of 32 envs exactly like a 4-warp block of the
+ * narrow builds, with the substep replaced by its phase-split form; warpgroups 1..3 serve it. */
+template <int NJL, bool LIMITS>
+__global__ void __launch_bounds__(kWThreads, 1) wide_step_kernel(const __grid_constant__ StepArgs args) {
+  extern __shared__ __align__(16) unsigned char wide_raw[];
+  WideShared& S = *reinterpret_cast<WideShared*>(wide_raw);
+  __shared__ Smem sm;
+  __shared__ __align__(16) StageTile stage[4];
+  if (blockIdx.x * kWEnvs >= args.n) return;      /* padding blocks of an experiment grid (SOLO_GRID_MIN) */
+  const SimConst& sc = args.sc;
+  {
+    const float* src = reinterpret_cast<const float*>(&args.mc.leg[0]);
+    float* dst = reinterpret_cast<float*>(&sm.leg[0]);
+    for (int i = threadIdx.x; i < (int)(sizeof(LegConst) * 4 / sizeof(float)); i += kWThreads) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int nsub = (args.mode == MODE_SUBSTEP) ? 1 : sc.frame_skip;
+  const int wg = threadIdx.x >> 7, t4 = threadIdx.x & (kWE4 - 1);
+  if (wg == 0) {
+    wide_regs_grow();
+    const int tid = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int wslot = blockIdx.x * 4 + wib;
+    EnvLane<NJL> L;
+    step_load<NJL>(args, wslot, tid, stage[wib], L);
+    for (int s = 0; s < nsub; s++) {                /* frame_skip x p.stepSimulation() (solo.py:264-265) */
+      const bool torque_on = (s == 0) || sc.torque_hold; /* SURVEY F4 */
+      float tau_s[NJL];
+#pragma unroll
+      for (int k = 0; k < NJL; k++) tau_s[k] = torque_on ? L.tau[k] : 0.f;
+      wide_leg_substep<NJL, LIMITS>(sm.leg[L.leg], args.mc, sc, S, t4, L.leg, L.st, L.ln, tau_s, L.cforce, L.bk.nc_sum,
+                            L.bk.sweep_feet);
+    }
+    step_finish<NJL>(args, wslot, stage[wib], L);
+  } else {
+    wide_regs_shrink();
+    for (int s = 0; s < nsub; s++) wide_helper_substep<NJL>(sm.leg[t4 & 3], sc, S, t4, wg - 1);
   }
 }
 
@@ -737,7 +857,8 @@ __global__ void __launch_bounds__(kBlockThreads) actuator_kernel(const __grid_co
     float tau[NJL];
 #pragma unroll
     for (int k = 0; k < NJL; k++) tau[k] = actuator_torque(sc, ln.q[k], ln.qd[k], qdes[k], vdes[k], P[k], D[k], tff[k]);
-    group_substep<NJL>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet);
+    if (sc.joint_limits) group_substep<NJL, true>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet);
+    else group_substep<NJL, false>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet);
   }
   if (valid) {
     if (leg == 0) store_base(d.base, e, st, goal, potential);
@@ -785,10 +906,11 @@ __global__ void reset_kernel(const __grid_constant__ ResetArgs args) {
   EnvBook bk = d.book[e];
   begin_reset<NJL>(d, args.sc, args.D0, e, leg, args.env_id_offset + e, args.seed_lo, args.seed_hi,
                    d.mut[kMutGoalRadius], args.reset_simulate, args.force_settle, st, ln, cforce, goal, potential, bk);
-  if (!args.reset_simulate && args.obs != nullptr) {
+  if (!args.reset_simulate) {
     RowPieces<NJL> cur;
     make_pieces<NJL>(args.sc, st, ln, cforce, goal, cur);
-    write_obs<NJL>(d, args.sc, args.D0, args.D, e, leg, cur, args.obs);
+    store_pieces<NJL>(cur_row(d, args.D0, e), leg, args.sc.task, cur);
+    if (args.obs != nullptr) write_obs<NJL>(d, args.sc, args.D0, args.D, e, leg, cur, args.obs);
   }
   if (leg == 0) { store_base(d.base, e, st, goal, potential); d.book[e] = bk; }
 #pragma unroll
@@ -856,6 +978,7 @@ __global__ void set_state_kernel(DevArrays d, SimConst sc, int n, int D0, const 
   RowPieces<NJL> cur;
   make_pieces<NJL>(sc, st, ln, cforce, goal, cur);
   for (int h = 0; h < sc.H; h++) store_pieces<NJL>(hist_row(d, D0, h, e), leg, sc.task, cur);
+  store_pieces<NJL>(cur_row(d, D0, e), leg, sc.task, cur);
   potential = (sc.task == 2) ? calc_potential(st, goal) : 0.f;
   if (leg == 0) {
     store_base(d.base, e, st, goal, potential);
@@ -872,20 +995,25 @@ __global__ void set_state_kernel(DevArrays d, SimConst sc, int n, int D0, const 
   d.cforce[e * 4 + leg] = cforce;
 }
 
-__global__ void set_goal_kernel(DevArrays d, int n, const float* goals) {
+__global__ void set_goal_kernel(DevArrays d, int n, int njl, int D0, int task, const float* goals) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   float* b = d.base + (size_t)e * kBaseStride;
   b[kBaseGoal] = goals[2 * e]; b[kBaseGoal + 1] = goals[2 * e + 1];
   float dx = b[0] - goals[2 * e], dy = b[1] - goals[2 * e + 1];
   b[kBasePot] = sqrtf(dx * dx + dy * dy);
+  if (task == 2) {                                   /* the goal is part of the pointgoal state row (solo.py:337-340) */
+    float* row = cur_row(d, D0, e);
+    row[idx_pg(njl) + 2] = goals[2 * e] / 2.0f; row[idx_pg(njl) + 3] = goals[2 * e + 1] / 2.0f;
+  }
 }
 
 /* parity hook: overwrite the per-foot contact record (normal force, < 0 = no contact point) */
-__global__ void set_contacts_kernel(DevArrays d, int n, const float* force) {
+__global__ void set_contacts_kernel(DevArrays d, SimConst sc, int n, int njl, int D0, const float* force) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * 4) return;
   d.cforce[t] = force[t];
+  cur_row(d, D0, t >> 2)[idx_flag(njl, t & 3)] = contact_flag(sc, force[t]);
 }
 
 __global__ void work_kernel(DevArrays d, int n, int* out) {
@@ -1122,7 +1250,7 @@ struct SoloHandle {
   ModelConst mc;
   SimConst sc;
   int n, njl, nj, A, D0, D, device, K, cap;
-  int throughput;  /* which build of the step kernel this handle launches (choose_throughput) */
+  int variant;     /* which build of the step kernel this handle launches (choose_variant) */
   uint64_t seed;
   long long env_id_offset;
   float goal_radius;
@@ -1159,14 +1287,37 @@ static StepArgs make_step_args(SoloHandle* h, int mode, int n, const float* in, 
   a.force_settle = -1;
   return a;
 }
+static int grid_min() {
+  static int v = -1;
+  if (v < 0) { const char* ev = getenv("SOLO_GRID_MIN"); v = ev ? atoi(ev) : 0; }
+  return v;
+}
 template <int MINB, int WPB>
 static void launch_step_variant(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
-  const int blocks = (a.n + 8 * WPB - 1) / (8 * WPB);
-  if (h->njl == 3) step_kernel<3, MINB, WPB><<<blocks, kBlockThreads * WPB, 0, s>>>(a);
-  else step_kernel<2, MINB, WPB><<<blocks, kBlockThreads * WPB, 0, s>>>(a);
+  int blocks = (a.n + 8 * WPB - 1) / (8 * WPB);
+  if (blocks < grid_min()) blocks = grid_min();
+  const bool lim = h->sc.joint_limits != 0;
+  if (h->njl == 3) {
+    if (lim) step_kernel<3, MINB, WPB, true><<<blocks, kBlockThreads * WPB, 0, s>>>(a);
+    else step_kernel<3, MINB, WPB, false><<<blocks, kBlockThreads * WPB, 0, s>>>(a);
+  } else {
+    if (lim) step_kernel<2, MINB, WPB, true><<<blocks, kBlockThreads * WPB, 0, s>>>(a);
+    else step_kernel<2, MINB, WPB, false><<<blocks, kBlockThreads * WPB, 0, s>>>(a);
+  }
 }
 static void launch_step(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
-  if (h->throughput) launch_step_variant<2, 8>(h, a, s);
+  if (h->variant == VARIANT_WIDE) {
+    int blocks = (a.n + kWEnvs - 1) / kWEnvs;
+    if (blocks < grid_min()) blocks = grid_min();
+    const bool lim = h->sc.joint_limits != 0;
+    if (h->njl == 3) {
+      if (lim) wide_step_kernel<3, true><<<blocks, kWThreads, sizeof(WideShared), s>>>(a);
+      else wide_step_kernel<3, false><<<blocks, kWThreads, sizeof(WideShared), s>>>(a);
+    } else {
+      if (lim) wide_step_kernel<2, true><<<blocks, kWThreads, sizeof(WideShared), s>>>(a);
+      else wide_step_kernel<2, false><<<blocks, kWThreads, sizeof(WideShared), s>>>(a);
+    }
+  } else if (h->variant == VARIANT_THROUGHPUT) launch_step_variant<2, 8>(h, a, s);
   else launch_step_variant<1, 4>(h, a, s);
   h->launches++;
 }
@@ -1174,11 +1325,12 @@ static void launch_step(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
  * SOLO_STEP_VARIANT=latency|throughput overrides.  Results are bit-reproducible within a build
  * (and therefore across shardings that stay within one); the two builds differ in the last bits
  * because the compiler contracts and schedules the arithmetic differently. */
-static int choose_throughput(int n) {
+static int choose_variant(int n) {
   const char* ev = getenv("SOLO_STEP_VARIANT");
-  if (ev && ev[0] == 'l') return 0;
-  if (ev && ev[0] == 't') return 1;
-  return n > 8192;
+  if (ev && ev[0] == 'l') return VARIANT_LATENCY;
+  if (ev && ev[0] == 't') return VARIANT_THROUGHPUT;
+  if (ev && ev[0] == 'w') return VARIANT_WIDE;
+  return n > 8192 ? VARIANT_THROUGHPUT : VARIANT_LATENCY;
 }
 static ResetArgs make_reset_args(SoloHandle* h, int n, const uint8_t* mask, float* obs) {
   ResetArgs a;
@@ -1232,7 +1384,7 @@ const char* solo_last_error(const SoloHandle* h) { return h ? h->err.c_str() : g
 int solo_destroy(SoloHandle* h) {
   if (!h) return SOLO_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d.base); cudaFree(h->d.q); cudaFree(h->d.qd); cudaFree(h->d.cforce); cudaFree(h->d.hist);
+  cudaFree(h->d.base); cudaFree(h->d.q); cudaFree(h->d.qd); cudaFree(h->d.cforce); cudaFree(h->d.hist); cudaFree(h->d.currow);
   cudaFree(h->d.book); cudaFree(h->d.stats);
   cudaFree(h->d.rc_base); cudaFree(h->d.rc_q); cudaFree(h->d.rc_qd); cudaFree(h->d.rc_cforce); cudaFree(h->d.rc_hist);
   cudaFree(const_cast<float*>(h->d.mut));
@@ -1267,7 +1419,7 @@ int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_
   h->device = device; h->seed = seed; h->env_id_offset = env_id_offset;
   h->goal_radius = (float)params->goal_radius;
   h->was_reset = false; h->launches = 0;
-  h->throughput = choose_throughput(num_envs);
+  h->variant = choose_variant(num_envs);
   h->K = params->settle_max - params->settle_min; if (h->K < 1) h->K = 1;
   h->cap = num_envs > h->K ? num_envs : h->K;
   h->s_act = h->s_obs = h->s_rew = h->s_done = nullptr;
@@ -1289,6 +1441,13 @@ int solo_create(const SoloModelTable* model, const SoloSimParams* params, int32_
 static int allocate_and_prime(SoloHandle* h, const SoloSimParams* params) {
   const int H = params->num_history_stack;
   CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->variant == VARIANT_WIDE) {     /* 104 KB of exchange arrays: above the 48 KB default */
+    const int bytes = (int)sizeof(WideShared);
+    CUDA_TRY(h, cudaFuncSetAttribute(wide_step_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(wide_step_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(wide_step_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(wide_step_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  }
   const size_t cap = (size_t)h->cap;
   {
     float* mut = nullptr;
@@ -1302,6 +1461,8 @@ static int allocate_and_prime(SoloHandle* h, const SoloSimParams* params) {
   CUDA_TRY(h, cudaMalloc(&h->d.qd, cap * 4 * h->njl * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d.cforce, cap * 4 * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d.hist, (cap * (H > 0 ? H : 1)) * h->D0 * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d.currow, cap * h->D0 * sizeof(float)));
+  CUDA_TRY(h, cudaMemset(h->d.currow, 0, cap * h->D0 * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d.book, cap * sizeof(EnvBook)));
   CUDA_TRY(h, cudaMalloc(&h->d.stats, cap * sizeof(SoloEpisodeStats)));
   CUDA_TRY(h, cudaMalloc(&h->d.rc_base, (size_t)h->K * kBaseStride * sizeof(float)));
@@ -1343,6 +1504,7 @@ static int allocate_and_prime(SoloHandle* h, const SoloSimParams* params) {
     CUDA_TRY(h, cudaMemsetAsync(h->d.qd, 0, cap * 4 * h->njl * sizeof(float), s));
     CUDA_TRY(h, cudaMemsetAsync(h->d.cforce, 0, cap * 4 * sizeof(float), s));
     CUDA_TRY(h, cudaMemsetAsync(h->d.hist, 0, (cap * (H > 0 ? H : 1)) * h->D0 * sizeof(float), s));
+    CUDA_TRY(h, cudaMemsetAsync(h->d.currow, 0, cap * h->D0 * sizeof(float), s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     CUDA_TRY(h, cudaGetLastError());
   }
@@ -1455,7 +1617,7 @@ int solo_set_state(SoloHandle* h, const float* d_state, void* stream) {
 int solo_set_goals(SoloHandle* h, const float* d_goals, void* stream) {
   if (!h || !d_goals) return fail(h, SOLO_E_ARG, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
-  set_goal_kernel<<<(h->n + 127) / 128, 128, 0, s>>>(h->d, h->n, d_goals);
+  set_goal_kernel<<<(h->n + 127) / 128, 128, 0, s>>>(h->d, h->n, h->njl, h->D0, h->params.task, d_goals);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return SOLO_OK;
@@ -1472,7 +1634,7 @@ int solo_get_contacts(SoloHandle* h, float* d_out, void* stream) {
 
 int solo_set_contacts(SoloHandle* h, const float* d_force, void* stream) {
   if (!h || !d_force) return fail(h, SOLO_E_ARG, "null argument");
-  set_contacts_kernel<<<(h->n * 4 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d, h->n, d_force);
+  set_contacts_kernel<<<(h->n * 4 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d, h->sc, h->n, h->njl, h->D0, d_force);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return SOLO_OK;
@@ -1592,9 +1754,22 @@ int solo_gae(const float* d_rewards, const float* d_values, const float* d_masks
 
 int64_t solo_launch_count(const SoloHandle* h) { return h ? h->launches : 0; }
 
+#ifdef SOLO_TRACE
+/* tools only: copy the phase stamps of the last wide step to the host (int64 [1024][8]) */
+int solo_debug_wide_trace(long long* h_out) {
+  return cudaMemcpyFromSymbol(h_out, solo::g_wide_trace, sizeof(long long) * 1024 * 8) == cudaSuccess ? 0 : -3;
+}
+int solo_debug_narrow_trace(long long* h_out) {
+  return cudaMemcpyFromSymbol(h_out, solo::g_narrow_trace, sizeof(long long) * 1024 * 8 * 8) == cudaSuccess ? 0 : -3;
+}
+int solo_debug_wide_trace_helpers(long long* h_out) {
+  return cudaMemcpyFromSymbol(h_out, solo::g_wide_trace_h, sizeof(long long) * 1024 * 3 * 8) == cudaSuccess ? 0 : -3;
+}
+#endif
+
 const char* solo_step_variant(const SoloHandle* h) {
   if (!h) return "";
-  return h->throughput ? "throughput" : "latency";
+  return h->variant == VARIANT_WIDE ? "wide" : (h->variant == VARIANT_THROUGHPUT ? "throughput" : "latency");
 }
 
 }  // extern "C"

@@ -64,23 +64,38 @@ def line_chains(lib, mangled_hint):
     return chains
 
 
+SCOPES = [("solo_wide.cuh", "void wide_link("), ("solo_wide.cuh", "void wide_row("),
+          ("solo_wide.cuh", "void wide_leg_substep("), ("solo_wide.cuh", "void wide_helper_substep("),
+          ("solo_kernels.cu", "void contact_solve("), ("solo_kernels.cu", "void group_substep("),
+          ("solo_kernels.cu", "void step_load("), ("solo_kernels.cu", "void step_finish("),
+          ("solo_kernels.cu", ") step_kernel("), ("solo_kernels.cu", ") wide_step_kernel(")]
+
+
 def main():
     rep, lib = sys.argv[1], sys.argv[2]
     kernel = sys.argv[3] if len(sys.argv) > 3 else "step_kernel"
     skip = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     name, hdr, body = sass_page(rep, kernel, skip)
-    m = re.search(r"step_kernel<\(int\)(\d), \(int\)(\d)>", name)
-    hint = f"step_kernelILi{m.group(1)}ELi{m.group(2)}E" if m else "step_kernel"
+    m = re.search(r"(wide_)?step_kernel<\(int\)(\d)(?:, \(int\)(\d))?", name)
+    if m and m.group(1):
+        hint = f"wide_step_kernelILi{m.group(2)}E"
+    elif m:
+        hint = f"step_kernelILi{m.group(2)}ELi{m.group(3)}E"
+    else:
+        hint = "step_kernel"
     chains = line_chains(lib, hint)
-    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "solorl_b200", "csrc",
-                            "solo_kernels.cu")).read().splitlines()
-    # line range of group_substep and step_kernel bodies
-    def body_range(sig):
-        s = next(i for i, l in enumerate(src) if sig in l) + 1
+    csrc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "solorl_b200", "csrc")
+    files = {f: open(os.path.join(csrc, f)).read().splitlines() for f in ("solo_kernels.cu", "solo_wide.cuh")}
+
+    def body_range(f, sig):
+        src = files[f]
+        s = next((i for i, l in enumerate(src) if sig in l), None)
+        if s is None:
+            return None
+        s += 1
         e = next(i for i in range(s, len(src)) if src[i].startswith("}")) + 1
-        return s, e
-    gs = body_range("void group_substep(")
-    sk = body_range(") step_kernel(")
+        return f, s, e
+    scopes = [r for r in (body_range(f, sig) for f, sig in SCOPES) if r]
     base = int(body[0][0], 16)
     i_inst, i_samp = hdr.index("Instructions Executed"), hdr.index("# Samples")
     si = {s: hdr.index(s) for s in STALLS if s in hdr}
@@ -90,33 +105,34 @@ def main():
         off = int(r[0], 16) - base
         ch = chains.get(off, [])
         key = None
-        for f, l in ch:                       # innermost -> outermost: first frame inside group_substep wins
-            if f == "solo_kernels.cu" and gs[0] <= l <= gs[1]:
-                key = l
+        for f, l in ch:                       # innermost -> outermost: first frame inside a phase-level function wins
+            if any(f == sf and s0 <= l <= s1 for sf, s0, s1 in scopes):
+                key = (f, l)
                 break
         if key is None:
-            for f, l in ch:
-                if f == "solo_kernels.cu" and sk[0] <= l <= sk[1]:
-                    key = l
-            if key is None:
-                key = -1
+            key = ("", -1)
         a = agg[key]
         a["inst"] += int(r[i_inst]); a["samp"] += int(r[i_samp]); a["sass"] += 1
         for s, j in si.items():
             a[s] += int(r[j])
         tot_i += int(r[i_inst]); tot_s += int(r[i_samp])
+    tot_nb = tot_s - sum(a.get("stall_barrier", 0) for a in agg.values())
     print(f"# {name}: {len(body)} SASS instructions ({len(body) * 16 / 1024:.0f} KiB), "
-          f"{tot_i} warp instructions executed, {tot_s} stall samples")
-    print(f"# {'line':>5} {'sass':>6} {'inst%':>6} {'samp%':>6}  " + " ".join(f"{s[6:10]:>5}" for s in si) + "  source")
+          f"{tot_i} warp instructions executed, {tot_s} stall samples ({tot_nb:.0f} outside barriers)")
+    print(f"# samp% = share of all samples; work% = share of the samples that are not barrier waits")
+    print(f"# {'file:line':>20} {'sass':>6} {'inst%':>6} {'samp%':>6} {'work%':>6}  " + " ".join(f"{s[6:10]:>5}" for s in si) + "  source")
     for key in sorted(agg, key=lambda k: -agg[k]["samp"]):
         a = agg[key]
         if a["samp"] < 0.002 * tot_s and a["inst"] < 0.002 * tot_i:
             continue
-        text = src[key - 1].strip()[:70] if key > 0 else "(no line info)"
+        f, l = key
+        text = files[f][l - 1].strip()[:64] if l > 0 else "(no line info)"
         st = " ".join(f"{100 * a[s] / max(tot_s, 1):5.1f}" for s in si)
-        print(f"  {key:5d} {int(a['sass']):6d} {100 * a['inst'] / tot_i:6.1f} {100 * a['samp'] / max(tot_s, 1):6.1f}  {st}  {text}")
+        work = a["samp"] - a.get("stall_barrier", 0)
+        print(f"  {f[5:12] + ':' + str(l):>20} {int(a['sass']):6d} {100 * a['inst'] / tot_i:6.1f} {100 * a['samp'] / max(tot_s, 1):6.1f} "
+              f"{100 * work / max(tot_nb, 1):6.1f}  {st}  {text}")
     st = " ".join(f"{100 * sum(agg[k][s] for k in agg) / max(tot_s, 1):5.1f}" for s in si)
-    print(f"  total {len(body):6d} {100.0:6.1f} {100.0:6.1f}  {st}")
+    print(f"  {'total':>20} {len(body):6d} {100.0:6.1f} {100.0:6.1f} {100.0:6.1f}  {st}")
 
 
 if __name__ == "__main__":
