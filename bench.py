@@ -288,6 +288,75 @@ def time_policy_rollout(cfg, n, dev, rank, world, barrier, T=32, reps=10):
             "what": "policy act + env step + rollout-buffer append per step, device resident"}
 
 
+def time_ppo_train(cfg, n, dev, rank, world, barrier, T=32, updates=6):
+    """BASELINE.json configs[4]: PPO training throughput, env-steps/s over whole updates = T-step policy rollout
+    (one CUDA graph) + GAE kernel + the clipped-surrogate update (ppo_epoch x mini-batches, each one CUDA graph
+    with the gradient all-reduce inside) + the 3-scalar advantage all-reduce.  Timed with CUDA events, max over
+    ranks.  The share of the collective is measured by repeating the same updates with the gradient all-reduce
+    switched off (graphs re-captured): (t_with - t_without) / t_with."""
+    import torch
+    from solorl_b200.agents.policy import Policy
+    from solorl_b200.agents.ppo import PPO, broadcast_parameters
+    from solorl_b200.agents.storage import OPBuffer
+    from solorl_b200.agents.train import EpisodeTracker, Rollout
+    from solorl_b200.envs import make_vec_envs
+    torch.manual_seed(1 + rank)
+    envs = make_vec_envs(cfg, n, device=dev, seed=2, env_id_offset=rank * n)
+    ac = Policy(envs.observation_space.shape, envs.action_space, None, {"hidden_size": 64}).to(dev)
+    broadcast_parameters(ac)
+    hp = dict(clip_param=0.1, ppo_epoch=5, mini_batch_size=16384, value_loss_coef=0.5, entropy_coef=0.0)
+    agent = PPO(ac, hp["clip_param"], hp["ppo_epoch"], hp["mini_batch_size"], hp["value_loss_coef"], hp["entropy_coef"],
+                lr=3e-4, max_grad_norm=0.5)
+    buf = OPBuffer(T, n, envs.observation_space.shape, envs.action_space.shape[0], dev)
+    buf.obs[0].copy_(envs.reset_inplace())
+    ro = Rollout(envs, ac, buf, EpisodeTracker(dev), T, use_graph=True)
+
+    def one_update():
+        ro()
+        with torch.no_grad():
+            nv = ac.get_value(buf.obs[-1]).detach()
+        buf.compute_returns(nv, True, 0.99, 0.95)
+        agent.update(buf)
+        buf.reset()
+
+    def timed(k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            one_update()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / k
+
+    for _ in range(3):                       # eager warm-up steps + graph captures
+        one_update()
+    ms_with = timed(updates)
+    nccl_share = None
+    if world > 1:
+        agent.sync_enabled = False
+        agent._graph, agent._graph_key, agent._warm = None, None, 0
+        for _ in range(2):
+            one_update()
+        ms_without = timed(updates)
+        agent.sync_enabled = True
+        nccl_share = max(0.0, (ms_with - ms_without) / ms_with)
+    envs.close()
+    mb_steps = hp["ppo_epoch"] * (n * T // hp["mini_batch_size"])
+    return {"value": world * n * T / (ms_with * 1e-3), "unit": "env-steps/s", "ms_per_update": ms_with,
+            "rollout_steps": T, "mini_batch_steps_per_update": mb_steps, "hyper": hp,
+            "grad_allreduce": {"numel": agent.flat.numel, "bytes": agent.flat.numel * 4, "calls_per_update": mb_steps,
+                               "pack_unpack_kernels": 0, "share_of_update_time": nccl_share,
+                               "how": "same updates with the collective switched off, (t_with - t_without) / t_with"},
+            "what": "rollout (policy act + env step + buffer append, one CUDA graph) + GAE + PPO update incl. NCCL "
+                    "gradient and advantage all-reduce; whole updates, CUDA events, max over ranks"}
+
+
 def time_saturated(cfg, dev, n, steps=60):
     """Device-resident env-steps/s of the same workload at a batch that fills the GPU (several resident waves
     of the 16-warps-per-SM throughput build), with the work counters of that run."""
@@ -494,6 +563,14 @@ def run_ours(args):
         except Exception as e:      # the headline metric does not depend on it
             policy_rollout = {"error": repr(e)[:200]}
 
+    # ---- PPO training with the gradient all-reduce (BASELINE.json configs[4]); the one collective of the system ---
+    ppo_train = None
+    if not args.no_ppo_train:
+        try:
+            ppo_train = time_ppo_train(cfg, n, dev, rank, world, barrier)
+        except Exception as e:
+            ppo_train = {"error": repr(e)[:300]}
+
     # ---- the same kernel when the batch fills the machine (throughput build, 65536 envs): how far the code is
     #      from the FP32 peak once it is no longer limited by the 4096-env batch of the headline workload ------
     saturated = None
@@ -561,6 +638,7 @@ def run_ours(args):
         "roofline": roofline,
         "back_to_back_ms_per_step": b2b_ms, "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
         "policy_rollout": policy_rollout,
+        "ppo_train": ppo_train,
         "saturated": saturated,
     }
     if saturated and "flops_per_env_step" in saturated:
@@ -593,6 +671,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-policy-rollout", action="store_true")
+    ap.add_argument("--no-ppo-train", action="store_true")
     ap.add_argument("--no-saturated", action="store_true")
     ap.add_argument("--saturated-envs", type=int, default=65536)
     args = ap.parse_args()

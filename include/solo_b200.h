@@ -253,6 +253,12 @@ int solo_action_to_torque(SoloHandle* h, const float* d_actions, float* d_tau, v
  * d_cmd float[N, 5, nj] = q_des, v_des, P, D, tau_ff.  State is read back with solo_get_state. */
 int solo_actuator_step(SoloHandle* h, const float* d_cmd, int32_t n_ticks, void* stream);
 
+/* Gait envs: external force on the base for the following solo_actuator_step calls, d_force float[N, 3] in base
+ * (link-frame) axes, acting at the base origin -- the random pushes of baseControlEnv.py:276-289, which the
+ * external simulator applies with pyb.applyExternalForce(robot, -1, F, [0,0,0], LINK_FRAME) [3P].  Stays in
+ * force until overwritten; zero after solo_create.  solo_step / solo_substep ignore it. */
+int solo_set_external_force(SoloHandle* h, const float* d_force, void* stream);
+
 /* World-frame centres of the four foot collision spheres, d_out float[N, 4, 3]
  * (replaces get_feet_positions, baseControlEnv.py:410-414). */
 int solo_get_feet(SoloHandle* h, float* d_out, void* stream);

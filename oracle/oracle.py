@@ -77,6 +77,7 @@ def lib():
         L.oracle_substep.argtypes = [vp, dp]
         L.oracle_get_contacts.argtypes = [vp, dp]
         L.oracle_set_contacts.argtypes = [vp, dp]
+        L.oracle_set_external_force.argtypes = [vp, dp]
         ip = C.POINTER(C.c_int)
         L.oracle_contact_rows.argtypes = [vp, dp, dp, dp, dp, ip, ip, dp]
         L.oracle_contact_rows.restype = C.c_int
@@ -221,6 +222,11 @@ class OracleEnv:
         f = np.ascontiguousarray(force, dtype=np.float64)
         assert f.shape == (4,)
         self.L.oracle_set_contacts(self.h, _dp(f))
+
+    def set_external_force(self, f):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        assert f.shape == (3,)
+        self.L.oracle_set_external_force(self.h, _dp(f))
 
     def contact_rows(self, tau):
         """Constraint rows the next substep(tau) would build (env not advanced): dict with J, U [rows, 6+nj],

@@ -202,6 +202,7 @@ struct OracleEnv {
   int settle_last;
   int last_iters;        /* PGS iterations used by the last substep with contacts */
   int last_limit_rows;   /* joint-limit rows of the last substep */
+  v3 fext;               /* external force on the base, base axes, at the base origin (gait-env pushes) */
 };
 
 /* per-step workspace of the articulated-body algorithm, Bullet-style: every spatial
@@ -386,7 +387,7 @@ static void aba_forward(const OracleEnv* e, AbaWork* W, const double* tau, doubl
     for (int k = 0; k < 3; k++) f[k] = m->base_mass * gw[k];
     m3mulv(fl, W->E0, f);
     v6zero(W->Z0);
-    for (int k = 0; k < 3; k++) W->Z0[3 + k] = -fl[k];
+    for (int k = 0; k < 3; k++) W->Z0[3 + k] = -fl[k] - e->fext[k];   /* gravity + external push (base axes) */
     m3 Ib; m3sym6(Ib, m->base_inertia);
     body_bias(W->Z0, W->v0, m->base_mass, Ib, p->lin_damping, p->ang_damping);
     m6zero(W->IA0);
@@ -879,6 +880,8 @@ int oracle_contact_rows(const OracleEnv* e0, const double* tau, double* J, doubl
   return nr;
 }
 
+void oracle_set_external_force(OracleEnv* e, const double* f3) { for (int k = 0; k < 3; k++) e->fext[k] = f3[k]; }
+
 /* parity hook: overwrite the contact record (what p.getContactPoints returned, solo.py:313-317):
  * force[f] < 0 = no contact point on foot f */
 void oracle_set_contacts(OracleEnv* e, const double* force) {
@@ -984,6 +987,10 @@ void oracle_forward_dynamics_crba(OracleEnv* e, const double* tau, double* qdd, 
         te[k] = -Iww[k] * (p->ang_damping + p->ang_damping * wn);
       }
       fe[2] += mass * p->gravity_z;
+      if (b == 0) {                         /* external push on the base: base axes -> world, at the base origin */
+        v3 fw; m3mulv(fw, Rb, e->fext);
+        for (int k = 0; k < 3; k++) fe[k] += fw[k];
+      }
       v3cross(t, c, fe);
       for (int k = 0; k < 3; k++) { f[k] -= te[k] + t[k]; f[3 + k] -= fe[k]; }
     }

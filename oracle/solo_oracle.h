@@ -82,6 +82,8 @@ void oracle_substep(OracleEnv* e, const double* tau);
 /* contact record of the last substep: out[4][3] = flag, has_point, normal force */
 void oracle_get_contacts(const OracleEnv* e, double* out);
 void oracle_set_contacts(OracleEnv* e, const double* force4);
+/* external force on the base (base axes, at the base origin) for the following substeps; gait-env pushes */
+void oracle_set_external_force(OracleEnv* e, const double* f3);
 /* constraint rows of the next substep without advancing the env (see solo_oracle.c); J, U: [rows][6+nj] */
 int oracle_contact_rows(const OracleEnv* e, const double* tau, double* J, double* U, double* target,
                         int* kind, int* owner, double* vstar);

@@ -22,7 +22,7 @@ SYMBOLS = [
     "solo_set_state", "solo_set_goals", "solo_get_contacts", "solo_get_work_counters", "solo_forward_dynamics",
     "solo_substep", "solo_action_to_torque", "solo_episode_stats", "solo_set_goal_radius",
     "solo_gae", "solo_launch_count", "solo_actuator_step", "solo_get_feet",
-    "solo_accumulate_episode_stats", "solo_set_contacts", "solo_step_variant",
+    "solo_accumulate_episode_stats", "solo_set_contacts", "solo_step_variant", "solo_set_external_force",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
     L.solo_episode_stats.argtypes = [vp, fp, vp]
     L.solo_actuator_step.argtypes = [vp, fp, C.c_int32, vp]
     L.solo_get_feet.argtypes = [vp, fp, vp]
+    L.solo_set_external_force.argtypes = [vp, fp, vp]
     L.solo_accumulate_episode_stats.argtypes = [vp, fp, fp, vp]
     L.solo_set_goal_radius.argtypes = [vp, C.c_double]
     L.solo_gae.argtypes = [fp, fp, fp, fp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, vp]

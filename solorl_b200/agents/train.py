@@ -43,6 +43,21 @@ class EpisodeTracker:
         """In place: the tensor is baked into the captured rollout graph."""
         self.acc.copy_(self._init)
 
+    def update_from_tensors(self, done, episode_return, episode_length, success, last_reward):
+        """Envs without a C-ABI episode record (the gait-env shell keeps its episode sums as tensors): the same
+        accumulator filled with torch ops (no host sync)."""
+        m = (done > 0.5).double()
+        ret, ln = episode_return.double(), episode_length.double()
+        self.acc[0] += m.sum()
+        self.acc[1] += (m * last_reward.double()).sum()
+        self.acc[2] += (m * ret).sum()
+        self.acc[3] += (m * ln).sum()
+        self.acc[4] += (m * success.double()).sum()
+        big = torch.full_like(ret, float("inf"))
+        self.acc[10] = torch.minimum(self.acc[10], torch.where(m > 0, ret, big).min())
+        self.acc[11] = torch.maximum(self.acc[11], torch.where(m > 0, ret, -big).max())
+        self.acc[12] = torch.maximum(self.acc[12], (m * ln).max())
+
     def update(self, sim, done):
         if self.acc.is_cuda:
             sim.accumulate_episode_stats(done, self.acc)
@@ -83,16 +98,22 @@ class Rollout:
 
     def __init__(self, envs, actor_critic, buf, tracker, num_steps, use_graph=True):
         self.envs, self.ac, self.buf, self.tracker, self.T = envs, actor_critic, buf, tracker, num_steps
-        self.sim = envs.envs.venv.sim
+        self.venv = envs.envs.venv
+        self.sim = getattr(self.venv, "sim", None)       # None: the gait-env shell (its own tick-loop graph inside)
         self.graph = None
-        self.use_graph = use_graph
+        self.use_graph = use_graph and self.sim is not None
 
     def _run(self):
         for t in range(self.T):
             with torch.no_grad():
                 value, action, logp = self.ac.act(self.buf.obs[t])
                 obs, reward, done, _infos = self.envs.step_inplace(action)    # copied into buf right below
-                self.tracker.update(self.sim, done)
+                if self.sim is not None:
+                    self.tracker.update(self.sim, done)
+                else:
+                    li = self.venv.last_info
+                    self.tracker.update_from_tensors(done, li["episode_reward"], li["episode_length"], li["success"],
+                                                     reward.reshape(-1))
                 self.buf.append(obs, action, logp, value, reward, (1.0 - done).unsqueeze(-1))
 
     def __call__(self):
@@ -144,7 +165,8 @@ def train(args, config, env_constructor=SoloBaseEnv, writer=None):
 
     envs = make_vec_envs(config, N, env_constructor, args.gamma, device, seed=args.seed,
                          env_id_offset=rank * N)
-    action_dim = envs.action_space.shape[0]
+    discrete = envs.action_space.__class__.__name__ == "Discrete"
+    action_dim = 1 if discrete else envs.action_space.shape[0]        # storage_dim of agents/ppo/train.py:34-39
     base = torch.load(args.base_checkpoint, map_location=device) if args.base_checkpoint is not None else None
     actor_critic = Policy(envs.observation_space.shape, envs.action_space, base, {"hidden_size": args.hidden_size})
     actor_critic.to(device)
@@ -168,6 +190,7 @@ def train(args, config, env_constructor=SoloBaseEnv, writer=None):
         with torch.no_grad():
             next_value = actor_critic.get_value(buf.obs[-1]).detach()
         buf.compute_returns(next_value, args.use_gae, args.gamma, args.tau)
+        step_reward = buf.rewards.mean()           # mean reward per env step of this rollout (read only at log time)
         value_loss, action_loss, dist_entropy = agent.update(buf)
         buf.reset()
         if args.curriculum_schedule and (j + 1) % args.curriculum_schedule == 0:
@@ -181,7 +204,8 @@ def train(args, config, env_constructor=SoloBaseEnv, writer=None):
             st = tracker.fetch()
             elapsed = time.time() - start
             st.update(update=j, steps=total_num_steps, seconds=elapsed, fps=total_num_steps / max(elapsed, 1e-9),
-                      value_loss=value_loss, action_loss=action_loss, entropy=dist_entropy)
+                      value_loss=value_loss, action_loss=action_loss, entropy=dist_entropy,
+                      mean_step_reward=float(step_reward))
             history.append(st)
             last = st
             if rank == 0:

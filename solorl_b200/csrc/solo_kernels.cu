@@ -58,6 +58,10 @@ struct DevArrays {
   /* run-time mutable scalars, read by the kernels from device memory so that a captured CUDA graph of the
    * step sees later updates: [0] = pointgoal goal radius (increment_goal_radius, solo.py:332-334) */
   const float* mut;
+  /* gait envs: external force on the base, base axes, acting at the base origin ([3P] the random pushes of
+   * baseControlEnv.py:276-289 go through pyb.applyExternalForce(robot, -1, F, 0, LINK_FRAME)); [cap][4], zero by
+   * default; read by the actuator kernel only */
+  float* fext;
   int cap;
 };
 enum { kMutGoalRadius = 0, kMutCount = 4 };
@@ -518,7 +522,8 @@ __device__ __forceinline__ void contact_solve(const SimConst& sc, int leg, BaseS
 template <int NJL, bool LIMITS>
 __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelConst& mc, const SimConst& sc,
                                               int leg, BaseState& st, Lane<NJL>& ln, const float* tau, float& cforce,
-                                              int& nc_sum, int& sweep_feet, int g_trace_sub = 0) {
+                                              int& nc_sum, int& sweep_feet, int g_trace_sub = 0,
+                                              const float* fext = nullptr) {
   NSTAMP(0);
   BaseWork bw;
   base_prepare(st, bw);
@@ -528,6 +533,10 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
   sum4_sym6(IA);
 #pragma unroll
   for (int i = 0; i < 6; i++) pA[i] = sum4(pA[i]);
+  if (fext != nullptr) {               /* external force on the base (gait envs): enters the bias force with a minus */
+#pragma unroll
+    for (int i = 0; i < 3; i++) pA[3 + i] -= fext[i];
+  }
   base_solve(mc, sc, bw, IA, pA, a0);
   {
     float qdd[NJL], aw[3], al[3];
@@ -853,12 +862,14 @@ __global__ void __launch_bounds__(kBlockThreads) actuator_kernel(const __grid_co
     qdes[k] = c[k]; vdes[k] = c[nj + k]; P[k] = c[2 * nj + k]; D[k] = c[3 * nj + k]; tff[k] = c[4 * nj + k];
   }
   int nc_sum = 0, sweep_feet = 0;
+  const float4 fx = reinterpret_cast<const float4*>(d.fext)[e];
+  const float fext[3] = {fx.x, fx.y, fx.z};
   for (int s = 0; s < n_ticks; s++) {
     float tau[NJL];
 #pragma unroll
     for (int k = 0; k < NJL; k++) tau[k] = actuator_torque(sc, ln.q[k], ln.qd[k], qdes[k], vdes[k], P[k], D[k], tff[k]);
-    if (sc.joint_limits) group_substep<NJL, true>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet);
-    else group_substep<NJL, false>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet);
+    if (sc.joint_limits) group_substep<NJL, true>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet, 0, fext);
+    else group_substep<NJL, false>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet, 0, fext);
   }
   if (valid) {
     if (leg == 0) store_base(d.base, e, st, goal, potential);
@@ -1006,6 +1017,12 @@ __global__ void set_goal_kernel(DevArrays d, int n, int njl, int D0, int task, c
     float* row = cur_row(d, D0, e);
     row[idx_pg(njl) + 2] = goals[2 * e] / 2.0f; row[idx_pg(njl) + 3] = goals[2 * e + 1] / 2.0f;
   }
+}
+
+__global__ void set_fext_kernel(DevArrays d, int n, const float* f) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  reinterpret_cast<float4*>(d.fext)[e] = make_float4(f[3 * e], f[3 * e + 1], f[3 * e + 2], 0.f);
 }
 
 /* parity hook: overwrite the per-foot contact record (normal force, < 0 = no contact point) */
@@ -1384,7 +1401,7 @@ const char* solo_last_error(const SoloHandle* h) { return h ? h->err.c_str() : g
 int solo_destroy(SoloHandle* h) {
   if (!h) return SOLO_OK;
   cudaSetDevice(h->device);
-  cudaFree(h->d.base); cudaFree(h->d.q); cudaFree(h->d.qd); cudaFree(h->d.cforce); cudaFree(h->d.hist); cudaFree(h->d.currow);
+  cudaFree(h->d.base); cudaFree(h->d.q); cudaFree(h->d.qd); cudaFree(h->d.cforce); cudaFree(h->d.hist); cudaFree(h->d.currow); cudaFree(h->d.fext);
   cudaFree(h->d.book); cudaFree(h->d.stats);
   cudaFree(h->d.rc_base); cudaFree(h->d.rc_q); cudaFree(h->d.rc_qd); cudaFree(h->d.rc_cforce); cudaFree(h->d.rc_hist);
   cudaFree(const_cast<float*>(h->d.mut));
@@ -1461,6 +1478,8 @@ static int allocate_and_prime(SoloHandle* h, const SoloSimParams* params) {
   CUDA_TRY(h, cudaMalloc(&h->d.qd, cap * 4 * h->njl * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d.cforce, cap * 4 * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d.hist, (cap * (H > 0 ? H : 1)) * h->D0 * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc(&h->d.fext, cap * 4 * sizeof(float)));
+  CUDA_TRY(h, cudaMemset(h->d.fext, 0, cap * 4 * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d.currow, cap * h->D0 * sizeof(float)));
   CUDA_TRY(h, cudaMemset(h->d.currow, 0, cap * h->D0 * sizeof(float)));
   CUDA_TRY(h, cudaMalloc(&h->d.book, cap * sizeof(EnvBook)));
@@ -1676,6 +1695,14 @@ int solo_actuator_step(SoloHandle* h, const float* d_cmd, int32_t n_ticks, void*
   const int blocks = (h->n + 7) / 8;
   if (h->njl == 3) actuator_kernel<3><<<blocks, kBlockThreads, 0, s>>>(a, n_ticks);
   else actuator_kernel<2><<<blocks, kBlockThreads, 0, s>>>(a, n_ticks);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return SOLO_OK;
+}
+
+int solo_set_external_force(SoloHandle* h, const float* d_force, void* stream) {
+  if (!h || !d_force) return fail(h, SOLO_E_ARG, "null argument");
+  set_fext_kernel<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d, h->n, d_force);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return SOLO_OK;

@@ -38,6 +38,9 @@ COULOMB_TAU = 0.0477
 VISCOUS_B = 0.000135
 K_MOTOR = 4.81
 VMAX = 0.8                                   # :20
+MAXFORCE = 10                                # :21
+DEFAULTFORCE = (7, 10)                       # :25  [min, max] push magnitude in N
+PUSH_DURATIONS = (1000, 2000, 3000, 4000, 5000)   # :26  in controller ticks
 Q_INIT = (0.0, 0.7, -1.4, -0.0, 0.7, -1.4, 0.0, -0.7, +1.4, -0.0, -0.7, +1.4)   # :41
 # soloGaitEnvContact.py:11-20 (index 9 = the "-1" entry: no gait yet)
 GAIT_TABLE = ((1., 1., 1., 1.), (1., 1., 1., 0.), (1., 1., 0., 1.), (1., 0., 1., 1.), (0., 1., 1., 1.),
@@ -201,8 +204,7 @@ class SoloGaitVecEnv:
         self.episode_length = int(config.get("episode_length", 100))
         if not config.get("flat_ground", True):
             raise NotImplementedError("flat_ground: False")
-        if config.get("add_external_force", False):
-            raise NotImplementedError("add_external_force (random pushes, baseControlEnv.py:276-289)")
+        self.add_external_force = bool(config.get("add_external_force", False))       # baseControlEnv.py:54
         self.auto_vel_switch = bool(config.get("auto_vel_switch", True))
         self.vel_switch = int(config.get("vel_switch", 30))
         self.use_curriculum = bool(config.get("use_curriculum", False))
@@ -223,6 +225,7 @@ class SoloGaitVecEnv:
         # one stream per shard: ranks of a multi-GPU run (env_id_offset = rank * N) must not draw identical
         # velocity references / pushes
         self.gen = torch.Generator(device=dev).manual_seed(int(seed) * 1000003 + self.env_id_offset)
+        self.k_rl_ticks_total = 0
         self.timestep = torch.zeros(self.nenvs, dtype=torch.int32, device=dev)
         self.past_gaits = torch.full((self.nenvs, 3), 9, dtype=torch.long, device=dev)     # deque([-1,-1,-1])
         self.vel_ref = torch.zeros(self.nenvs, 6, **f)
@@ -230,6 +233,18 @@ class SoloGaitVecEnv:
         self.ep_reward = torch.zeros(self.nenvs, **f)
         self.ep_length = torch.zeros(self.nenvs, dtype=torch.int32, device=dev)
         self.dr = torch.zeros(self.nenvs, 3, **f)                      # Torque_pen, body_velocity, Energy_pen
+        # random pushes (baseControlEnv.py:117-123,276-289): one per episode, a force along one base axis with an
+        # integer magnitude in [min, max] N, from a random controller tick on, for 1000..5000 ticks
+        if self.add_external_force:
+            mm = (0, 2) if self.use_curriculum else DEFAULTFORCE
+        else:
+            mm = (0, 0)
+        self.min_max_force = [int(mm[0]), int(mm[1])]
+        self.k_tick = torch.zeros(self.nenvs, dtype=torch.int32, device=dev)             # controller.k
+        self.push_F = torch.zeros(self.nenvs, 3, **f)
+        self.push_start = torch.zeros(self.nenvs, dtype=torch.int32, device=dev)
+        self.push_dur = torch.ones(self.nenvs, dtype=torch.int32, device=dev)
+        self._durations = torch.tensor(PUSH_DURATIONS, dtype=torch.int32, device=dev)
         self.last_info = None
         self._was_reset = False
         self.cuda_graph = bool(cuda_graph)
@@ -240,6 +255,38 @@ class SoloGaitVecEnv:
         """new_random_vel (baseControlEnv.py:29-32): uniform in +-max_velocity times the module mask."""
         v = (torch.rand(n, 6, device=self.device, generator=self.gen) - 0.5) * 2 * self.max_velocity
         return v * self.vel_mask
+
+    def _create_force_function(self, sel):
+        """create_force_function (baseControlEnv.py:276-289) for the envs in `sel` (bool [N]); tensors are updated
+        in place because the captured tick loop reads them."""
+        n, dev, g = self.nenvs, self.device, self.gen
+        lo, hi = self.min_max_force
+        axis = torch.randint(0, 3, (n,), device=dev, generator=g)
+        mag = torch.randint(lo, hi + 1, (n,), device=dev, generator=g).float()        # np.random.randint(min, max + 1)
+        sign = torch.randint(0, 2, (n,), device=dev, generator=g).float() * 2 - 1
+        F = torch.zeros(n, 3, device=dev)
+        F.scatter_(1, axis.unsqueeze(1), mag.unsqueeze(1))
+        F = F * torch.stack([sign, sign, torch.ones_like(sign)], dim=1)                # F *= [sign, sign, 1]
+        hi_start = max(500, int(self.k_rl * self.episode_length * (2.0 / 3.0)))
+        start = torch.randint(500, hi_start + 1, (n,), device=dev, generator=g, dtype=torch.int32)
+        dur = self._durations[torch.randint(0, len(PUSH_DURATIONS), (n,), device=dev, generator=g)]
+        m = sel.unsqueeze(1)
+        self.push_F.copy_(torch.where(m, F, self.push_F))
+        self.push_start.copy_(torch.where(sel, start, self.push_start))
+        self.push_dur.copy_(torch.where(sel, dur, self.push_dur))
+
+    def _apply_force(self):
+        """_apply_force(controller.k): [3P] PyBulletSimulator.apply_external_force(k, start, duration, F, M) of the
+        external simulator -- while start <= k <= start + duration the base is pushed with alpha(k) F in its own
+        frame, alpha = 16 s^2 (1 - s)^2, s = (k - start) / duration (a smooth bump that peaks at 1 mid-way;
+        restated from the LAAS quadruped-reactive-walking sources, not in the reference tree)."""
+        ev = (self.k_tick - self.push_start).float()
+        dur = self.push_dur.float()
+        inside = (ev >= 0) & (ev <= dur)
+        sfrac = (ev / dur).clamp(0.0, 1.0)
+        alpha = 16.0 * sfrac * sfrac * (1.0 - sfrac) * (1.0 - sfrac)
+        self.robot.sim.set_external_force(torch.where(inside.unsqueeze(1), alpha.unsqueeze(1) * self.push_F,
+                                                      torch.zeros_like(self.push_F)))
 
     def get_base_vel(self):
         return torch.cat([self.robot.b_baseVel, self.robot.baseAngularVelocity], dim=1)   # :447-451
@@ -275,6 +322,9 @@ class SoloGaitVecEnv:
         if self.auto_vel_switch:
             self.vel_ref = torch.where(sel.unsqueeze(1), self._new_random_vel(self.nenvs), self.vel_ref)
         self.past_gaits = torch.where(sel.unsqueeze(1), torch.full_like(self.past_gaits, 9), self.past_gaits)
+        self.k_tick.masked_fill_(sel, 0)                                           # a fresh controller: k = 0
+        if self.add_external_force:
+            self._create_force_function(sel)                                        # baseControlEnv.py:213
         self.timestep.masked_fill_(sel, 0)
         self.ep_reward = torch.where(sel, torch.zeros_like(self.ep_reward), self.ep_reward)
         self.ep_length = torch.where(sel, torch.zeros_like(self.ep_length), self.ep_length)
@@ -320,6 +370,9 @@ class SoloGaitVecEnv:
         vel_pen = torch.zeros_like(torque_pen)
         joints_power = torch.zeros(self.nenvs, 12, device=self.device)
         for _ in range(self.k_rl):
+            if self.add_external_force:
+                self._apply_force()                                                  # baseControlEnv.py:148
+            self.k_tick += 1
             r.UpdateMeasurment()
             P, D, q_des, v_des, tau_ff = self.controller.compute(r, a, self.vel_ref)
             r.SetDesiredJointPDgains(P, D)
@@ -369,9 +422,12 @@ class SoloGaitVecEnv:
         self._graph.replay()
         return tuple(t.clone() for t in self._g_out)
 
-    def increment_curriculum(self, val=0.1):                                       # :314-323
-        if self.use_curriculum:
-            self.max_velocity = float(np.clip(self.max_velocity + val, 0.0, VMAX))
+    def increment_curriculum(self, val=0.1):                                       # :321-328
+        if not self.use_curriculum:
+            return
+        self.max_velocity = float(np.clip(self.max_velocity + val, 0.0, VMAX))
+        lo, hi = self.min_max_force                                                # increment min and max force
+        self.min_max_force = [int(np.clip(lo + 1, 0, MAXFORCE - 2)), int(np.clip(hi + 1, 0, MAXFORCE))]
 
     def get_torques(self):
         return self.robot.tau_ff

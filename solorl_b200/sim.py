@@ -175,6 +175,11 @@ class SoloSim:
         c = self._f32(cmd, (self.n, 5, self.nj))
         _lib.check(self.L.solo_actuator_step(self.h, _ptr(c), int(n_ticks), self._stream()), self.h)
 
+    def set_external_force(self, force):
+        """Base-frame force [N,3] at the base origin for the following actuator_step calls (gait-env pushes)."""
+        f = self._f32(force, (self.n, 3))
+        _lib.check(self.L.solo_set_external_force(self.h, _ptr(f), self._stream()), self.h)
+
     def get_feet(self):
         out = torch.empty(self.n, 4, 3, dtype=torch.float32, device=self.device)
         _lib.check(self.L.solo_get_feet(self.h, _ptr(out), self._stream()), self.h)

@@ -235,3 +235,35 @@ def test_td3_cli_defaults_are_the_reference_defaults():
                save_interval=2000, task=None)                                     # train_td3.py:10-39
     for k, v in ref.items():
         assert getattr(a, k) == v, k
+
+
+def test_flat_parameter_buffers_alias_and_change_nothing():
+    """PPO keeps parameters and gradients as views of two flat buffers (one all-reduce, no pack / unpack): the
+    update is bit-identical to the unflattened one, the views survive it, state_dict keys are unchanged."""
+    from solorl_b200.agents.policy import Policy
+    from solorl_b200.agents.ppo import PPO
+    from solorl_b200.agents.storage import OPBuffer
+    from solorl_b200.envs import Box
+    T, N, D, A = 6, 8, 10, 4
+    ws = []
+    for flat in (True, False):
+        torch.manual_seed(3)
+        ac = Policy((D,), Box(-np.ones(A), np.ones(A)), None, {"hidden_size": 16})
+        keys = list(ac.state_dict().keys())
+        agent = PPO(ac, 0.1, 2, 16, 0.5, 0.01, lr=1e-3, max_grad_norm=0.5, flat_parameters=flat)
+        assert list(ac.state_dict().keys()) == keys
+        buf = OPBuffer(T, N, (D,), A, "cpu")
+        g = torch.Generator().manual_seed(5)
+        for t in (buf.obs, buf.actions, buf.rewards, buf.value_preds, buf.returns):
+            t.copy_(torch.randn(t.shape, generator=g))
+        buf.action_log_probs.copy_(torch.randn(buf.action_log_probs.shape, generator=g) * 0.1 - 5.0)
+        torch.manual_seed(11)                      # the mini-batch permutation
+        agent.update(buf)
+        if flat:
+            assert agent.flat.intact() and agent.flat.numel == sum(p.numel() for p in ac.parameters())
+            assert torch.equal(agent.flat.data, torch.cat([p.detach().reshape(-1) for p in ac.parameters()]))
+            sd = {k: v.clone() for k, v in ac.state_dict().items()}
+            ac.load_state_dict(sd)                 # an in-place copy: the views must survive it
+            assert agent.flat.intact()
+        ws.append(torch.cat([p.detach().reshape(-1) for p in ac.parameters()]).clone())
+    assert torch.equal(ws[0], ws[1])

@@ -94,10 +94,15 @@ def main(argv=None):
                 writer = SummaryWriter(args.logdir)
             except Exception:       # tensorboard is optional in this image
                 os.makedirs(args.logdir, exist_ok=True)
-    if args.env_name != "base":
-        raise NotImplementedError(f"Error Env {args.env_name} not found! (only 'base' = SoloBaseEnv is built; the gait "
-                                  "and timing envs wrap an external MPC controller that the reference does not ship)")
-    out = ppo.train(args, config, SoloBaseEnv, writer)
+    if args.env_name == "base":                                   # training/train_ppo.py:76-99
+        env_constructor = SoloBaseEnv
+    elif args.env_name == "contact":
+        from solorl_b200.gait import SoloGaitEnvContact as env_constructor
+    else:
+        raise NotImplementedError(f"Error Env {args.env_name} not found! ('base' = SoloBaseEnv and 'contact' = "
+                                  "SoloGaitEnvContact are built; the other gait / timing envs cannot be constructed "
+                                  "from any shipped config)")
+    out = ppo.train(args, config, env_constructor, writer)
     if world > 1:
         torch.distributed.destroy_process_group()
     return out
