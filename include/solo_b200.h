@@ -147,6 +147,16 @@ typedef struct SoloSimParams {
   double joint_limit_erp;         /* 0.2   btContactSolverInfo::m_erp */
   double joint_limit_max_impulse; /* 100   btMultiBodyConstraint m_maxAppliedImpulse default */
   double split_impulse_threshold; /* -0.04 violations deeper than this get no positional correction */
+  /* contacts of links other than the feet with the flat ground: in Bullet a collapsed robot rests
+   * on its knees / base box (convex hulls of the visual meshes, solo.py:72-73) and may stay above the z < 0.05
+   * termination height (baseEnv.py:169) until the timeout.  Collision primitives, [3P] stand-ins for those hulls:
+   * one sphere per knee (centre = KFE joint origin, on the lower-leg link) and the eight corners of the base box
+   * (points).  Contact points are ordered feet, knees, lower base corners, upper base corners (leg order inside
+   * each group); normals of all points are swept first, then the friction pair of each point. */
+  int32_t body_contacts;          /* 0: feet only (default, what round 1 built); 1: knees and base corners too */
+  double knee_radius;             /* 0.015: the lower-leg mesh reaches 0.0135 m above the KFE axis */
+  double base_half_x, base_half_y;/* 0.2241 x 0.1095 (Solo12), 0.212 x 0.1046 (Solo8) */
+  double base_z_lo, base_z_hi;    /* -0.025, 0.028: bottom / top of the base box relative to the base origin */
 } SoloSimParams;
 
 /* Per-env episode record, valid for envs whose `done` was 1 at the last step

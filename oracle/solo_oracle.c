@@ -18,7 +18,8 @@
 
 #define MAXL SOLO_MAX_LINKS
 #define MAXD ORACLE_MAX_DOF
-#define MAXROWS (3 * SOLO_MAX_FEET)
+#define MAXC 16                   /* contact points: 4 feet + 4 knees + 8 base-box corners */
+#define MAXROWS (3 * MAXC)
 
 /* ------------------------------------------------------------------ small algebra */
 typedef double v3[3];
@@ -259,6 +260,10 @@ void oracle_default_params(SoloSimParams* p) {
   p->joint_limit_erp = 0.2;
   p->joint_limit_max_impulse = 100.0;
   p->split_impulse_threshold = -0.04;
+  p->body_contacts = 0;
+  p->knee_radius = 0.015;          /* lower-leg mesh z in [-0.1675, 0.0135] about the KFE axis */
+  p->base_half_x = 0.2241; p->base_half_y = 0.1095;   /* Solo12 base box (Solo8: 0.212 x 0.1046) */
+  p->base_z_lo = -0.025; p->base_z_hi = 0.028;
 }
 
 OracleEnv* oracle_env_create(const SoloModelTable* m, const SoloSimParams* p, uint64_t seed,
@@ -479,7 +484,7 @@ static void aba_forward(const OracleEnv* e, AbaWork* W, const double* tau, doubl
  * on link `link` ([3P] btMultiBody::calcAccelerationDeltasMultiDof); uses the articulated
  * inertias cached by the last aba_forward.  out[6+nj] = (dw world, dv world, dqd). */
 /* velocity response (angular, linear, joints) to a unit impulse along `dir` at world point `pt` of `link`
- * (link < 0: none) plus a generalized impulse `jimp` on the joint of `jlink` (jlink < 0: none) */
+ * (link -1: the base, -2: none) plus a generalized impulse `jimp` on the joint of `jlink` (jlink < 0: none) */
 static void impulse_response(const OracleEnv* e, const AbaWork* W, int link, const v3 pt,
                              const v3 dir, int jlink, double jimp, double* out) {
   const SoloModelTable* m = &e->m;
@@ -495,6 +500,13 @@ static void impulse_response(const OracleEnv* e, const AbaWork* W, int link, con
     m3Tmulv(fl, W->Rw[link], dir);
     m3Tmulv(tl, W->Rw[link], tq);
     for (int k = 0; k < 3; k++) { Zt[link][k] = -tl[k]; Zt[link][3 + k] = -fl[k]; }
+  } else if (link == -1) {              /* a point of the base itself (base COM = base origin) */
+    v3 arm, tq, fl, tl;
+    for (int k = 0; k < 3; k++) arm[k] = pt[k] - e->pos[k];
+    v3cross(tq, arm, dir);
+    m3mulv(fl, W->E0, dir);
+    m3mulv(tl, W->E0, tq);
+    for (int k = 0; k < 3; k++) { Z0[k] = -tl[k]; Z0[3 + k] = -fl[k]; }
   }
   for (int i = n - 1; i >= 0; i--) {
     int par = m->parent[i];
@@ -577,6 +589,59 @@ static void plane_space(const v3 n, v3 p, v3 q) {
   }
 }
 
+/* Collision detection on the current poses against the plane z = 0: the foot spheres, and with body_contacts the
+ * knee spheres (centre = KFE joint origin, carried by the lower-leg link) and the corners of the base box.
+ * Point order = row order: feet, knees, lower base corners, upper base corners, legs 0..3 inside each group.
+ * Out per contact: link (-1 = base), index of the point (0..15), distance, world contact point. */
+static int detect_contacts(const OracleEnv* e, const AbaWork* W, int* clink, int* cidx, double* cdist, v3* cpt) {
+  const SoloModelTable* m = &e->m;
+  const SoloSimParams* p = &e->p;
+  int nc = 0;
+  for (int f = 0; f < m->num_feet; f++) {
+    int l = m->foot_link[f];
+    v3 off, c;
+    for (int k = 0; k < 3; k++) off[k] = m->foot_center[f][k] - m->com[l][k];
+    m3mulv(c, W->Rw[l], off);
+    for (int k = 0; k < 3; k++) c[k] += W->pw[l][k];
+    double dist = c[2] - m->foot_radius;
+    if (dist < p->contact_margin) {
+      clink[nc] = l; cidx[nc] = f; cdist[nc] = dist;
+      v3set(cpt[nc], c[0], c[1], c[2] - m->foot_radius);
+      nc++;
+    }
+  }
+  if (!p->body_contacts) return nc;
+  for (int f = 0; f < m->num_feet; f++) {               /* knees */
+    int l = m->parent[m->foot_link[f]];                  /* lower leg: its joint origin is the KFE axis */
+    v3 off, c;
+    for (int k = 0; k < 3; k++) off[k] = -m->com[l][k];
+    m3mulv(c, W->Rw[l], off);
+    for (int k = 0; k < 3; k++) c[k] += W->pw[l][k];
+    double dist = c[2] - p->knee_radius;
+    if (dist < p->contact_margin) {
+      clink[nc] = l; cidx[nc] = 4 + f; cdist[nc] = dist;
+      v3set(cpt[nc], c[0], c[1], c[2] - p->knee_radius);
+      nc++;
+    }
+  }
+  m3 Rb;
+  quat_to_m3(Rb, e->quat);
+  for (int g = 0; g < 2; g++)                             /* lower corners, then upper corners */
+    for (int f = 0; f < 4; f++) {                         /* leg order: FL (+x,+y) FR (+x,-y) HL (-x,+y) HR (-x,-y) */
+      v3 loc = {(f < 2 ? 1.0 : -1.0) * p->base_half_x, ((f & 1) ? -1.0 : 1.0) * p->base_half_y,
+                g == 0 ? p->base_z_lo : p->base_z_hi};
+      v3 c;
+      m3mulv(c, Rb, loc);
+      for (int k = 0; k < 3; k++) c[k] += e->pos[k];
+      if (c[2] < p->contact_margin) {
+        clink[nc] = -1; cidx[nc] = 8 + 4 * g + f; cdist[nc] = c[2];
+        v3cpy(cpt[nc], c);
+        nc++;
+      }
+    }
+  return nc;
+}
+
 typedef struct {
   double J[MAXD], u[MAXD]; /* jacobian row and M^-1 J^T */
   double dinv, rhs, lambda;
@@ -603,25 +668,12 @@ void oracle_substep(OracleEnv* e, const double* tau) {
   aba_forward(e, &W, tau, qdd);
 
   /* 1 contacts at the pre-integration poses */
-  int nc = 0, cfoot[SOLO_MAX_FEET];
-  v3 cpt[SOLO_MAX_FEET];
-  double cdist[SOLO_MAX_FEET];
-  const v3 nrm = {0, 0, 1};
-  for (int f = 0; f < m->num_feet; f++) {
-    int l = m->foot_link[f];
-    v3 off, c;
-    for (int k = 0; k < 3; k++) off[k] = m->foot_center[f][k] - m->com[l][k];
-    m3mulv(c, W.Rw[l], off);
-    for (int k = 0; k < 3; k++) c[k] += W.pw[l][k];
-    double dist = c[2] - m->foot_radius;
-    e->c_has[f] = 0; e->c_force[f] = 0;
-    if (dist < p->contact_margin) {
-      cfoot[nc] = f; cdist[nc] = dist;
-      v3set(cpt[nc], c[0], c[1], c[2] - m->foot_radius);
-      e->c_has[f] = 1;
-      nc++;
-    }
-  }
+  int clink[MAXC], cidx[MAXC];
+  v3 cpt[MAXC];
+  double cdist[MAXC];
+  for (int f = 0; f < m->num_feet; f++) { e->c_has[f] = 0; e->c_force[f] = 0; }
+  const int nc = detect_contacts(e, &W, clink, cidx, cdist, cpt);
+  for (int c = 0; c < nc; c++) if (cidx[c] < 4) e->c_has[cidx[c]] = 1;
   /* 1b joint-limit rows ([3P] btMultiBodyJointLimitConstraint::createConstraintRows): a row exists while the
    * joint position (start of the step) is at or beyond a limit; row 0 = lower bound, row 1 = upper bound */
   int nl = 0, llink[2 * MAXL];
@@ -666,11 +718,12 @@ void oracle_substep(OracleEnv* e, const double* tau) {
     for (int j = 0; j < e->nj; j++) vel[6 + j] = e->qd[e->link_of_dof[j]];
     for (int k = 0; k < nd; k++) dv[k] = 0;
     /* 3 rows */
-    Row rn[SOLO_MAX_FEET], rf[SOLO_MAX_FEET][2];
+    Row rn[MAXC], rf[MAXC][2];
+    const v3 nrm = {0, 0, 1};
     v3 t1, t2;
     plane_space(nrm, t1, t2);
     for (int c = 0; c < nc; c++) {
-      int l = m->foot_link[cfoot[c]];
+      int l = clink[c];
       const double* dirs[3] = {nrm, t1, t2};
       for (int r = 0; r < 3; r++) {
         Row* row = (r == 0) ? &rn[c] : &rf[c][r - 1];
@@ -697,7 +750,7 @@ void oracle_substep(OracleEnv* e, const double* tau) {
       const v3 zero = {0, 0, 0};
       for (int k = 0; k < nd; k++) row->J[k] = 0;
       row->J[dof] = ldir[c];
-      impulse_response(e, &W, -1, zero, zero, llink[c], ldir[c], row->u);
+      impulse_response(e, &W, -2, zero, zero, llink[c], ldir[c], row->u);
       row->dinv = 1.0 / rowdot(nd, row->J, row->u);
       const double rel_vel = rowdot(nd, row->J, vel);
       /* splitImpulse is on by default: shallow violations combine the ERP push-back with the velocity target,
@@ -780,7 +833,7 @@ void oracle_substep(OracleEnv* e, const double* tau) {
     for (int k = 0; k < 3; k++) { e->vang[k] += dv[k]; e->vlin[k] += dv[3 + k]; }
     for (int j = 0; j < e->nj; j++) e->qd[e->link_of_dof[j]] += dv[6 + j];
     clamp_velocities(e);
-    for (int c = 0; c < nc; c++) e->c_force[cfoot[c]] = rn[c].lambda / dt;
+    for (int c = 0; c < nc; c++) if (cidx[c] < 4) e->c_force[cidx[c]] = rn[c].lambda / dt;
   }
   /* integrate positions ([3P] btMultiBody::stepPositionsMultiDof) */
   for (int k = 0; k < 3; k++) e->pos[k] += dt * e->vlin[k];
@@ -814,23 +867,11 @@ int oracle_contact_rows(const OracleEnv* e0, const double* tau, double* J, doubl
   int nd = 6 + e->nj, nr = 0;
   double qdd[MAXD], dt = p->dt;
   aba_forward(e, &W, tau, qdd);
-  int nc = 0, cfoot[SOLO_MAX_FEET];
-  v3 cpt[SOLO_MAX_FEET];
-  double cdist[SOLO_MAX_FEET];
+  int clink[MAXC], cidx[MAXC];
+  v3 cpt[MAXC];
+  double cdist[MAXC];
   const v3 nrm = {0, 0, 1};
-  for (int f = 0; f < m->num_feet; f++) {
-    int l = m->foot_link[f];
-    v3 off, c;
-    for (int k = 0; k < 3; k++) off[k] = m->foot_center[f][k] - m->com[l][k];
-    m3mulv(c, W.Rw[l], off);
-    for (int k = 0; k < 3; k++) c[k] += W.pw[l][k];
-    double dist = c[2] - m->foot_radius;
-    if (dist < p->contact_margin) {
-      cfoot[nc] = f; cdist[nc] = dist;
-      v3set(cpt[nc], c[0], c[1], c[2] - m->foot_radius);
-      nc++;
-    }
-  }
+  const int nc = detect_contacts(e, &W, clink, cidx, cdist, cpt);
   for (int k = 0; k < 3; k++) { e->vang[k] += dt * qdd[k]; e->vlin[k] += dt * qdd[3 + k]; }
   for (int j = 0; j < e->nj; j++) e->qd[e->link_of_dof[j]] += dt * qdd[6 + j];
   clamp_velocities(e);
@@ -850,7 +891,7 @@ int oracle_contact_rows(const OracleEnv* e0, const double* tau, double* J, doubl
         const v3 zero = {0, 0, 0};
         for (int k = 0; k < nd; k++) Jr[k] = 0;
         Jr[6 + e->dof_of_link[i]] = dir;
-        impulse_response(e, &W, -1, zero, zero, i, dir, Ur);
+        impulse_response(e, &W, -2, zero, zero, i, dir, Ur);
         const double positional = (pen > p->split_impulse_threshold) ? -pen * p->joint_limit_erp / dt : 0.0;
         target[nr] = positional - rowdot(nd, Jr, vel);
         kind[nr] = 3; owner[nr] = i; nr++;
@@ -862,7 +903,7 @@ int oracle_contact_rows(const OracleEnv* e0, const double* tau, double* J, doubl
   const double* dirs[3] = {nrm, t1, t2};
   for (int pass = 0; pass < 2; pass++) {          /* normals of every contact first, then the friction pairs */
     for (int c = 0; c < nc; c++) {
-      int l = m->foot_link[cfoot[c]];
+      int l = clink[c];
       for (int r = (pass == 0 ? 0 : 1); r < (pass == 0 ? 1 : 3); r++) {
         double* Jr = J + (size_t)nr * nd; double* Ur = U + (size_t)nr * nd;
         contact_jacobian(e, &W, l, cpt[c], dirs[r], Jr);

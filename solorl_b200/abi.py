@@ -88,6 +88,12 @@ class SoloSimParams(C.Structure):
         ("joint_limit_erp", C.c_double),
         ("joint_limit_max_impulse", C.c_double),
         ("split_impulse_threshold", C.c_double),
+        ("body_contacts", C.c_int32),
+        ("knee_radius", C.c_double),
+        ("base_half_x", C.c_double),
+        ("base_half_y", C.c_double),
+        ("base_z_lo", C.c_double),
+        ("base_z_hi", C.c_double),
     ]
 
 
@@ -195,6 +201,10 @@ def default_params() -> SoloSimParams:
     p.joint_limit_erp = 0.2
     p.joint_limit_max_impulse = 100.0
     p.split_impulse_threshold = -0.04
+    p.body_contacts = 0
+    p.knee_radius = 0.015
+    p.base_half_x, p.base_half_y = 0.2241, 0.1095
+    p.base_z_lo, p.base_z_hi = -0.025, 0.028
     return p
 
 
@@ -232,13 +242,16 @@ def params_from_config(config: dict, model: Optional[SoloModel] = None) -> SoloS
     p.pointgoal_dt = p.frame_skip * p.dt
     if model is not None:
         p.joint_state_limit = model.joint_state_limit          # solo.py:109
+    if model is not None and model.nj == 8:                    # base box extents per robot
+        p.base_half_x, p.base_half_y = 0.212, 0.1046
     for k in ("torque_hold", "solver_iters", "cone_friction", "joint_limits", "limit_rows_per_leg", "settle_min",
-              "settle_max"):
+              "settle_max", "body_contacts"):
         if k in config:
             setattr(p, k, int(config[k]))
     for k in ("contact_erp", "contact_margin", "contact_slop", "friction", "lin_damping",
               "ang_damping", "goal_radius", "solver_residual_threshold", "joint_limit_erp",
-              "joint_limit_max_impulse", "split_impulse_threshold"):
+              "joint_limit_max_impulse", "split_impulse_threshold", "knee_radius", "base_half_x", "base_half_y",
+              "base_z_lo", "base_z_hi"):
         if k in config:
             setattr(p, k, float(config[k]))
     rm = config.get("reset_mode", "cached")

@@ -141,6 +141,10 @@ inline void fill_default_params(SoloSimParams* p) {
   p->joint_limit_erp = 0.2;
   p->joint_limit_max_impulse = 100.0;
   p->split_impulse_threshold = -0.04;
+  p->body_contacts = 0;
+  p->knee_radius = 0.015;
+  p->base_half_x = 0.2241; p->base_half_y = 0.1095;
+  p->base_z_lo = -0.025; p->base_z_hi = 0.028;
 }
 
 }  // namespace solo

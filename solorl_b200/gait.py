@@ -401,11 +401,12 @@ class SoloGaitVecEnv:
                 self._g_vel = torch.zeros(self.nenvs, 6, device=self.device)
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
-                state = self.robot.sim.get_state().clone()
+                state, k0 = self.robot.sim.get_state().clone(), self.k_tick.clone()
                 with torch.cuda.stream(s):                    # warm-up on a side stream, then restore the state
                     self._ticks(a)
                 torch.cuda.current_stream().wait_stream(s)
                 self.robot.sim.set_state(state)
+                self.k_tick.copy_(k0)                         # the warm-up must not advance the controller clock
                 real_vel = self.vel_ref
                 self.vel_ref = self._g_vel                    # the captured program reads the static copies
                 g = torch.cuda.CUDAGraph()
