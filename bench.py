@@ -412,6 +412,38 @@ def time_reset_simulate(cfg, n, dev, steps=40):
     return out
 
 
+def time_body_contacts(cfg, n, dev, steps=60):
+    """The headline workload with body_contacts on (knees and base-box corners collide with the ground, SURVEY
+    section 8f n4): a collapsed robot rests on its body instead of sinking to the z < 0.05 termination, so fewer
+    envs reset per step and the envs that lie on the ground solve 5-11 contact points on the general path."""
+    import torch
+    from solorl_b200.envs import SoloVecEnv
+    env = SoloVecEnv(dict(cfg, body_contacts=1), n, device=dev, seed=1)
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(11)
+    acts = [torch.rand(n, env.sim.act_dim, device=dev, generator=g) * 2 - 1 for _ in range(8)]
+    for i in range(100):                 # past the first collapses: the work mix is the steady one
+        env.sim.step(acts[i % 8])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dones, pts = 0.0, []
+    e0.record()
+    for i in range(steps):
+        env.sim.step(acts[i % 8])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    for i in range(8):
+        env.sim.step(acts[i % 8])
+        dones += float(env.sim.done.sum())
+        pts.append(float(env.sim.get_work_counters()[:, 0].float().mean()) / 4.0)
+    out = {"value": n / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
+           "resets_per_env_step": dones / (8 * n), "mean_contact_points_per_substep": float(np.mean(pts)),
+           "what": "device-resident, back-to-back steps, body_contacts = 1 (step_kernel<..., BODY>)"}
+    env.close()
+    return out
+
+
 def time_gae(dev, peaks, T=400, N=ENVS_PER_GPU, reps=20):
     """HBM view of the rollout-buffer kernel (solo_gae): 20 B per (t, env)."""
     import torch
@@ -649,6 +681,10 @@ def run_ours(args):
             line["reset_mode_simulate"] = time_reset_simulate(cfg, n, dev)
         except Exception as e:
             line["reset_mode_simulate"] = {"error": repr(e)[:200]}
+        try:
+            line["body_contacts"] = time_body_contacts(cfg, n, dev)
+        except Exception as e:
+            line["body_contacts"] = {"error": repr(e)[:200]}
         try:
             line["gae"] = time_gae(dev, peaks)
         except Exception as e:

@@ -232,7 +232,7 @@ class OracleEnv:
         """Constraint rows the next substep(tau) would build (env not advanced): dict with J, U [rows, 6+nj],
         target, kind (0 normal, 1/2 friction, 3 joint limit), owner, vstar."""
         tau = np.ascontiguousarray(tau, dtype=np.float64)
-        nd, cap = 6 + self.nj, 12 + 2 * self.nj
+        nd, cap = 6 + self.nj, 48 + 2 * self.nj      # 16 contact points x 3 rows + two limit rows per joint
         J, U = np.zeros((cap, nd)), np.zeros((cap, nd))
         target, vstar = np.zeros(cap), np.zeros(nd)
         kind, owner = np.zeros(cap, np.int32), np.zeros(cap, np.int32)

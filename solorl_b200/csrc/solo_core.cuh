@@ -78,6 +78,9 @@ struct SimConst {
   /* joint-limit rows ([3P] btMultiBodyJointLimitConstraint) */
   int joint_limits;
   float lim_erp, lim_max_impulse, lim_split_thr;
+  /* contacts of knees and base-box corners with the ground (solo_body.cuh) */
+  int body_contacts;
+  float knee_r, base_hx, base_hy, base_zlo, base_zhi;
 };
 
 /* ------------------------------------------------------------------ small helpers */

@@ -119,6 +119,12 @@ inline int build_sim_const(const SoloSimParams& p, SimConst& sc, std::string& er
   sc.joint_limits = p.joint_limits ? 1 : 0;
   sc.lim_erp = (float)p.joint_limit_erp; sc.lim_max_impulse = (float)p.joint_limit_max_impulse;
   sc.lim_split_thr = (float)p.split_impulse_threshold;
+  sc.body_contacts = p.body_contacts ? 1 : 0;
+  if (p.body_contacts && (p.knee_radius < 0 || p.base_half_x <= 0 || p.base_half_y <= 0 || p.base_z_hi < p.base_z_lo)) {
+    err = "body_contacts: bad knee radius / base box"; return SOLO_E_ARG;
+  }
+  sc.knee_r = (float)p.knee_radius; sc.base_hx = (float)p.base_half_x; sc.base_hy = (float)p.base_half_y;
+  sc.base_zlo = (float)p.base_z_lo; sc.base_zhi = (float)p.base_z_hi;
   return SOLO_OK;
 }
 

@@ -30,6 +30,7 @@
 
 #include "../../include/solo_b200.h"
 #include "solo_core.cuh"
+#include "solo_body.cuh"
 #include "solo_env.cuh"
 #include "solo_host_model.h"
 
@@ -421,13 +422,31 @@ __device__ int g_trace_substep;
 /* Second half of a substep for the four lanes of an env: contact / joint-limit rows -> Delassus rows ->
  * projected Gauss-Seidel -> impulses -> position update.  In: ln (P, K, sP, Lm, b, dist, active of the own
  * foot and the ABA by-products r, ax, h, invD), bw (pre-update rotation, LDL factor), the limit-row selection. */
-template <int NJL, bool LIMITS>
+template <int NJL, bool LIMITS, bool BODY>
 __device__ __forceinline__ void contact_solve(const SimConst& sc, int leg, BaseState& st, const BaseWork& bw,
-                                              Lane<NJL>& ln, bool lim_any, int kL, float dirL, float penL,
-                                              float& cforce, int& nc_sum, int& sweep_feet, int g_trace_sub = 0) {
+                                              Lane<NJL>& ln, bool lim_env, int kL, float dirL, float penL,
+                                              float& cforce, int& nc_sum, int& sweep_feet, int g_trace_sub = 0,
+                                              float* body_rows = nullptr) {
   const unsigned kFull = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned gbase = lane & ~3u;
+  /* BODY (SoloSimParams.body_contacts): an env with a knee or a base corner on the ground solves ALL its rows on
+   * the general path (solo_body.cuh) and takes part in the register path below with empty rows -- the choice is
+   * per env, never per warp, so an env's result does not depend on its neighbours */
+  const int foot_on = ln.active;
+  bool body_env = false;
+  unsigned pmask = 0;
+  BodyLaneGeom<NJL> bg;
+  if (BODY) {
+    body_lane_geometry<NJL>(sc, st, bw, ln, leg, bg);
+    const unsigned bf = __ballot_sync(kFull, foot_on != 0), bk = __ballot_sync(kFull, bg.kn_on);
+    const unsigned b0 = __ballot_sync(kFull, bg.c_on[0]), b1 = __ballot_sync(kFull, bg.c_on[1]);
+    pmask = ((bf >> gbase) & 0xFu) | (((bk >> gbase) & 0xFu) << 4) | (((b0 >> gbase) & 0xFu) << 8) |
+            (((b1 >> gbase) & 0xFu) << 12);
+    body_env = (pmask >> 4) != 0;
+    if (body_env) ln.active = 0;
+  }
+  const bool lim_any = lim_env && !body_env;
   const unsigned ball = __ballot_sync(kFull, ln.active != 0);
   const unsigned amask = (ball >> gbase) & 0xFu;                 /* feet in contact of this env */
   const unsigned wmask = (ball | (ball >> 4) | (ball >> 8) | (ball >> 12) | (ball >> 16) | (ball >> 20) |
@@ -509,6 +528,35 @@ __device__ __forceinline__ void contact_solve(const SimConst& sc, int leg, BaseS
     mat3_mulv(bw.R, dv0 + 3, dvl);
     base_add_velocity(sc, st, dw, dvl, 1.0f);
   }
+  if (BODY) {
+    ln.active = foot_on;
+    if (body_env) {                  /* diverges between the envs of a warp; the four lanes of an env stay together */
+      const unsigned gmask = 0xFu << gbase;
+      const unsigned lm_all = (__ballot_sync(gmask, lim_env) >> gbase) & 0xFu;
+      LimitRow<NJL> lr;
+      lr.active = 0;
+      if (LIMITS) limit_setup<NJL>(sc, bw, ln, lim_env, kL, dirL, penL, lr);
+      body_lane_fill<NJL>(sc, st, bw, ln, LIMITS ? &lr : nullptr, leg, foot_on != 0, bg, body_rows);
+      __syncwarp(gmask);
+      float dv0[6], s[4][3];
+      const int sweeps = sc.cone ? body_pgs<true>(body_rows, lm_all, pmask, sc, gmask, dv0, s)
+                                 : body_pgs<false>(body_rows, lm_all, pmask, sc, gmask, dv0, s);
+      float us[NJL];
+#pragma unroll
+      for (int k = 0; k < NJL; k++) us[k] = body_sel(s, leg, k);
+      body_apply_leg<NJL>(ln, sc, us, dv0);
+      float dw[3], dvl[3];
+      mat3_mulv(bw.R, dv0, dw);
+      mat3_mulv(bw.R, dv0 + 3, dvl);
+      base_add_velocity(sc, st, dw, dvl, 1.0f);
+      lam3[0] = foot_on ? body_rows[body_slot(leg, 0) * kBodyRowW + kBrLam] : 0.f;
+      const int np = __popc(pmask);
+      nc_sum += np;
+      sweep_feet += np * sweeps;
+      __syncwarp(gmask);
+    }
+    __syncwarp();
+  }
   cforce = ln.active ? lam3[0] * sc.inv_dt : -1.0f;
   integrate_base(sc, st);
 #pragma unroll
@@ -519,11 +567,11 @@ __device__ __forceinline__ void contact_solve(const SimConst& sc, int leg, BaseS
  * Control flow is kept WARP-uniform (skip masks and the sweep-loop exit are warp votes, envs that
  * have nothing to do contribute exact zeros) so that every shuffle is a full-mask shuffle of a
  * converged warp: group-masked shuffles cost a WARPSYNC each and let the 4-lane groups drift apart. */
-template <int NJL, bool LIMITS>
+template <int NJL, bool LIMITS, bool BODY = false>
 __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelConst& mc, const SimConst& sc,
                                               int leg, BaseState& st, Lane<NJL>& ln, const float* tau, float& cforce,
                                               int& nc_sum, int& sweep_feet, int g_trace_sub = 0,
-                                              const float* fext = nullptr) {
+                                              const float* fext = nullptr, float* body_rows = nullptr) {
   NSTAMP(0);
   BaseWork bw;
   base_prepare(st, bw);
@@ -553,7 +601,8 @@ __device__ __forceinline__ void group_substep(const LegConst& lc, const ModelCon
   int kL;
   float dirL, penL;
   const bool lim_any = LIMITS && limit_select<NJL>(sc, ln, kL, dirL, penL);
-  contact_solve<NJL, LIMITS>(sc, leg, st, bw, ln, lim_any, kL, dirL, penL, cforce, nc_sum, sweep_feet, g_trace_sub);
+  contact_solve<NJL, LIMITS, BODY>(sc, leg, st, bw, ln, lim_any, kL, dirL, penL, cforce, nc_sum, sweep_feet, g_trace_sub,
+                                   body_rows);
   NSTAMP(5);
 }
 
@@ -752,10 +801,11 @@ __device__ __forceinline__ void step_finish(const StepArgs& args, int wslot, Sta
  * (profiles/r1_sweep_wpb.txt: +6 % at 4096 envs, +38 % at 64k envs against one warp per block).
  * Eight envs per warp always: narrower warps were measured slower at every size
  * (profiles/r1_sweep_epw.txt). */
-template <int NJL, int MINB, int WPB, bool LIMITS>
+template <int NJL, int MINB, int WPB, bool LIMITS, bool BODY = false>
 __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const __grid_constant__ StepArgs args) {
   __shared__ Smem sm;
   __shared__ __align__(16) StageTile stage[WPB];
+  extern __shared__ __align__(16) float body_smem[];   /* BODY: the row records of the block's 8 x WPB envs */
   if (blockIdx.x * (8 * WPB) >= args.n) return;   /* padding blocks of an experiment grid (SOLO_GRID_MIN) */
   const int tid = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;      /* warp in block */
@@ -776,7 +826,9 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
     float tau_s[NJL];
 #pragma unroll
     for (int k = 0; k < NJL; k++) tau_s[k] = torque_on ? L.tau[k] : 0.f;
-    group_substep<NJL, LIMITS>(sm.leg[L.leg], args.mc, sc, L.leg, L.st, L.ln, tau_s, L.cforce, L.bk.nc_sum, L.bk.sweep_feet, s);
+    group_substep<NJL, LIMITS, BODY>(sm.leg[L.leg], args.mc, sc, L.leg, L.st, L.ln, tau_s, L.cforce, L.bk.nc_sum,
+                                     L.bk.sweep_feet, s, nullptr,
+                                     BODY ? body_smem + (size_t)(wib * 8 + L.el) * kBodyEnvStride : nullptr);
   }
   step_finish<NJL>(args, wslot, stage[wib], L);
 }
@@ -1322,7 +1374,27 @@ static void launch_step_variant(SoloHandle* h, const StepArgs& a, cudaStream_t s
     else step_kernel<2, MINB, WPB, false><<<blocks, kBlockThreads * WPB, 0, s>>>(a);
   }
 }
+/* body_contacts: the latency shape (4 warps per block) plus the row records in dynamic shared memory */
+constexpr int kBodyWPB = 4;
+constexpr size_t kBodySmemBytes = (size_t)kBodyWPB * 8 * kBodyEnvStride * sizeof(float);
+static void launch_step_body(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
+  int blocks = (a.n + 8 * kBodyWPB - 1) / (8 * kBodyWPB);
+  const bool lim = h->sc.joint_limits != 0;
+  const int threads = kBlockThreads * kBodyWPB;
+  if (h->njl == 3) {
+    if (lim) step_kernel<3, 1, kBodyWPB, true, true><<<blocks, threads, kBodySmemBytes, s>>>(a);
+    else step_kernel<3, 1, kBodyWPB, false, true><<<blocks, threads, kBodySmemBytes, s>>>(a);
+  } else {
+    if (lim) step_kernel<2, 1, kBodyWPB, true, true><<<blocks, threads, kBodySmemBytes, s>>>(a);
+    else step_kernel<2, 1, kBodyWPB, false, true><<<blocks, threads, kBodySmemBytes, s>>>(a);
+  }
+}
 static void launch_step(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
+  if (h->sc.body_contacts) {
+    launch_step_body(h, a, s);
+    h->launches++;
+    return;
+  }
   if (h->variant == VARIANT_WIDE) {
     int blocks = (a.n + kWEnvs - 1) / kWEnvs;
     if (blocks < grid_min()) blocks = grid_min();
@@ -1464,6 +1536,13 @@ static int allocate_and_prime(SoloHandle* h, const SoloSimParams* params) {
     CUDA_TRY(h, cudaFuncSetAttribute(wide_step_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CUDA_TRY(h, cudaFuncSetAttribute(wide_step_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CUDA_TRY(h, cudaFuncSetAttribute(wide_step_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  }
+  if (h->sc.body_contacts) {            /* 160 KB of row records: above the 48 KB default */
+    const int bytes = (int)kBodySmemBytes;
+    CUDA_TRY(h, cudaFuncSetAttribute(step_kernel<3, 1, kBodyWPB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(step_kernel<3, 1, kBodyWPB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(step_kernel<2, 1, kBodyWPB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_TRY(h, cudaFuncSetAttribute(step_kernel<2, 1, kBodyWPB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
   const size_t cap = (size_t)h->cap;
   {

@@ -226,7 +226,7 @@ __device__ __forceinline__ void wide_leg_substep(const LegConst& lc, const Model
     ln.b[m] = have_rows ? S.b[m][t4] : 0.f;
   }
   contact_local_block<NJL>(ln);
-  contact_solve<NJL, LIMITS>(sc, leg, st, bw, ln, lim_any, kL, dirL, penL, cforce, nc_sum, sweep_feet);
+  contact_solve<NJL, LIMITS, false>(sc, leg, st, bw, ln, lim_any, kL, dirL, penL, cforce, nc_sum, sweep_feet);
   WIDE_STAMP(6);
 }
 

@@ -17,7 +17,7 @@ _lib = None
 def build():
     srcs = [os.path.join(_HERE, "solo_emu.cpp")] + [
         os.path.join(_ROOT, "solorl_b200", "csrc", f)
-        for f in ("solo_core.cuh", "solo_env.cuh", "solo_host_model.h")] + [
+        for f in ("solo_core.cuh", "solo_env.cuh", "solo_host_model.h", "solo_body.cuh")] + [
         os.path.join(_ROOT, "include", "solo_b200.h")]
     if (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs):
         os.makedirs(os.path.dirname(_LIB), exist_ok=True)

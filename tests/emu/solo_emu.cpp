@@ -12,6 +12,7 @@
 
 #include "../../include/solo_b200.h"
 #include "../../solorl_b200/csrc/solo_core.cuh"
+#include "../../solorl_b200/csrc/solo_body.cuh"
 #include "../../solorl_b200/csrc/solo_env.cuh"
 #include "../../solorl_b200/csrc/solo_host_model.h"
 
@@ -100,6 +101,40 @@ static void emu_substep(Emu* e, const float* tau) {
     const bool any = limit_select<NJL>(sc, ln[l], kL, dirL, penL);
     limit_setup<NJL>(sc, bw, ln[l], any, kL, dirL, penL, lr[l]);
     if (any) lmask |= 1u << l;
+  }
+  /* knees / base corners on the ground: the env takes the general row-record path (solo_body.cuh) */
+  unsigned pmask = mask;
+  BodyLaneGeom<NJL> bg[4];
+  if (sc.body_contacts) {
+    for (int l = 0; l < 4; l++) {
+      body_lane_geometry<NJL>(sc, e->st, bw, ln[l], l, bg[l]);
+      if (bg[l].kn_on) pmask |= 1u << (4 + l);
+      if (bg[l].c_on[0]) pmask |= 1u << (8 + l);
+      if (bg[l].c_on[1]) pmask |= 1u << (12 + l);
+    }
+  }
+  const bool body_env = (pmask >> 4) != 0;
+  if (body_env) {
+    static float rows[kBodyEnvStride];
+    for (int l = 0; l < 4; l++) body_lane_fill<NJL>(sc, e->st, bw, ln[l], &lr[l], l, ln[l].active != 0, bg[l], rows);
+    float dv0[6], s[4][3];
+    if (sc.cone) body_pgs<true>(rows, lmask, pmask, sc, 0xFu, dv0, s);
+    else body_pgs<false>(rows, lmask, pmask, sc, 0xFu, dv0, s);
+    for (int l = 0; l < 4; l++) {
+      body_apply_leg<NJL>(ln[l], sc, s[l], dv0);
+      e->cforce[l] = ln[l].active ? rows[body_slot(l, 0) * kBodyRowW + kBrLam] * sc.inv_dt : -1.0f;
+    }
+    float dw[3], dvl[3];
+    mat3_mulv(bw.R, dv0, dw);
+    mat3_mulv(bw.R, dv0 + 3, dvl);
+    base_add_velocity(sc, e->st, dw, dvl, 1.0f);
+    integrate_base(sc, e->st);
+    for (int l = 0; l < 4; l++)
+      for (int k = 0; k < NJL; k++) {
+        e->qd[l * NJL + k] = ln[l].qd[k];
+        e->q[l * NJL + k] = ln[l].q[k] + sc.dt * ln[l].qd[k];
+      }
+    return;
   }
   if (lmask) {
     PgsLane4 pl[4];

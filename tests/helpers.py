@@ -129,3 +129,35 @@ def limit_states(rng, n, nj, airborne=False):
             s[i, 13 + j] = sign * (10.0 + depth)
             s[i, 13 + nj + j] = rng.normal() * 6.0
     return s.astype(np.float32).astype(np.float64)
+
+
+def collapsed_states(rng, n, robot, upside_down=0.15, params=None):
+    """States of a robot that has fallen, harvested from ORACLE trajectories with body contacts on: dropped from
+    0.2-0.3 m with a random tilt (a fraction on its back) and random leg posture under small random torques, then
+    60-300 substeps later.  Knees and base-box corners rest on (or are about to hit) the ground in most samples: the
+    inputs of the body-contact (SoloSimParams.body_contacts) parity tests."""
+    from oracle.oracle import OracleEnv, default_params
+    from solorl_b200.model import SoloModel
+    m = SoloModel.builtin(robot)
+    p = params
+    if p is None:
+        p = default_params()
+        p.body_contacts = 1
+        if robot == "solo8":
+            p.base_half_x, p.base_half_y = 0.212, 0.1046
+    e = OracleEnv(m, p)
+    nj = e.nj
+    out = np.zeros((n, 13 + 2 * nj))
+    for i in range(n):
+        s = np.zeros(13 + 2 * nj)
+        s[2] = rng.uniform(0.2, 0.3)
+        roll = rng.normal() * 0.5 + (np.pi if rng.random() < upside_down else 0.0)
+        pitch, yaw = rng.normal() * 0.4, rng.uniform(-np.pi, np.pi)
+        cr, sr, cp, sp, cy, sy = np.cos(roll / 2), np.sin(roll / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(yaw / 2), np.sin(yaw / 2)
+        s[3:7] = [sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy]
+        s[13:13 + nj] = rng.uniform(-2.0, 2.0, size=nj)
+        e.set_state(s)
+        for _ in range(int(rng.integers(60, 300))):
+            e.substep(rng.normal(size=nj) * 0.3)
+        out[i] = e.get_state()
+    return out.astype(np.float32).astype(np.float64)

@@ -939,3 +939,116 @@ def test_reset_cache_with_a_settle_span_above_one_warp():
         o2, r2, d2, _ = e2.step(a)
         assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
     e1.close(); e2.close()
+
+
+# ---- contacts of knees / base-box corners (SoloSimParams.body_contacts) ------------------
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_body_contact_substep_1e3(robot):
+    """A fallen robot resting on knees and base-box corners (5-11 contact points, some joint-limit rows), mixed in
+    one batch with robots standing on their feet -- warps whose envs split over the register path and the general
+    row-record path (solo_body.cuh).  Identical fp32-representable states injected before every substep; same 1e-3
+    bound as foot contact, contact sets exact.
+
+    A robot lying on the ground is a redundant contact problem (two points of one rigid lower leg, four corners of
+    one base: a singular Delassus matrix), and Bullet's 50 unconverged Gauss-Seidel sweeps are then not a stable
+    map: in a few per cent of these samples the fp64 oracle ITSELF moves by 1e-2..1 when its input state is
+    perturbed by one fp32 ulp.  Those samples cannot be held to 1e-3 by any fp32 implementation, so -- as in
+    test_contact_substep_singular_reset_pose -- the bound is widened by the oracle's measured sensitivity, and the
+    test asserts the 1e-3 bound on the stable samples (> 90 %), with the exceedance budget stated at the end."""
+    from oracle.oracle import OracleVecEnv
+    from tests.helpers import collapsed_states
+    rng = np.random.default_rng(61)
+    n = 96
+    sim, m, p = make_sim(robot, n, body_contacts=1)
+    assert p.body_contacts == 1
+    nj = sim.nj
+    ov, ov2 = OracleVecEnv(m, p, n), OracleVecEnv(m, p, n)
+    cur = np.concatenate([collapsed_states(rng, 64, robot, params=p), stance_states(rng, 32, nj)])
+    cur = cur[rng.permutation(n)]
+    errs, sens, ferr, body, total = [], [], [], 0, 0
+    for t in range(30):
+        tau = (rng.normal(size=(n, nj)) * 0.5).astype(np.float32).astype(np.float64)
+        sim.set_state(cuda(cur))
+        sim.substep(cuda(tau))
+        nxt = sim.get_state().cpu().numpy().astype(np.float64)
+        con = sim.get_contacts().cpu().numpy()
+        ref, rcon, _ = ov.substep_from(cur, tau)
+        pert, _, _ = ov2.substep_from(cur * (1 + rng.choice([-1, 1], size=cur.shape) * 6e-8), tau)
+        assert (rcon[:, :, 1] == con[:, :, 1]).all()
+        scale = np.maximum(1.0, np.abs(ref))
+        errs.append((np.abs(ref - nxt) / scale).max(axis=1))
+        sens.append((np.abs(ref - pert) / scale).max(axis=1))
+        ferr.append(np.abs(rcon[:, :, 2] - con[:, :, 2]).max(axis=1) / max(1.0, rcon[:, :, 2].max()))
+        body += int((cur[:, 2] < 0.12).sum()); total += n          # base low: knees / corners within the margin
+        cur = nxt
+    errs, sens, ferr = np.concatenate(errs), np.concatenate(sens), np.concatenate(ferr)
+    stable = sens < 1e-4
+    print(f"[{robot}] {len(errs)} substeps, {body} of a fallen robot, {stable.mean():.3f} stable: median {np.median(errs):.2e} "
+          f"p99 {np.quantile(errs, 0.99):.2e}; stable samples max {errs[stable].max():.2e}, foot force error / largest "
+          f"force {ferr[stable].max():.2e}; unstable samples: oracle sensitivity up to {sens.max():.2e}, error up to {errs.max():.2e}")
+    assert body > 0.5 * total and stable.mean() > 0.9
+    assert np.isfinite(nxt).all()
+    assert np.median(errs) < 1e-4 and np.quantile(errs, 0.99) < TOL_CONTACT
+    # one random perturbation is a noisy estimate of a sample's sensitivity, so the stable set is held to the same
+    # kind of budget as the 1e5-substep foot-contact test: at most 2 in 10^3 above 1e-3, none above 1e-2
+    rate = float((errs[stable] > TOL_CONTACT).mean())
+    assert rate <= 2e-3 and errs[stable].max() < 1e-2, (rate, errs[stable].max())
+    assert ferr[stable].max() < 2e-2
+    sim.close()
+
+
+def test_body_contacts_result_does_not_depend_on_the_neighbours():
+    """The register path / general path choice is per env: env i of a mixed batch (fallen and standing robots in
+    the same warps) equals, bitwise, the same env stepped in a batch of its own."""
+    from tests.helpers import collapsed_states
+    rng = np.random.default_rng(62)
+    n = 64
+    sim, m, p = make_sim("solo12", n, body_contacts=1)
+    nj = sim.nj
+    cur = np.concatenate([collapsed_states(rng, 40, "solo12", params=p), stance_states(rng, 24, nj)])
+    cur = cur[rng.permutation(n)]
+    tau = (rng.normal(size=(n, nj)) * 0.5)
+    sim.set_state(cuda(cur))
+    for _ in range(4):
+        sim.substep(cuda(tau))
+    full = sim.get_state()
+    sim.close()
+    for i in (0, 5, 17, 40, 63):
+        one, _, _ = make_sim("solo12", 1, body_contacts=1)
+        one.set_state(cuda(cur[i:i + 1]))
+        for _ in range(4):
+            one.substep(cuda(tau[i:i + 1]))
+        assert torch.equal(one.get_state()[0], full[i]), i
+        one.close()
+
+
+def test_body_contacts_keep_a_fallen_robot_on_the_ground_at_full_size():
+    """4096 envs under random actions with body contacts on: no base ever sinks below the ground (with feet-only
+    contacts a collapsed robot falls through to z < 0 before the z < 0.05 termination fires), every state stays
+    finite, and switching body contacts on leaves a standing robot bit-identical."""
+    from solorl_b200.envs import SoloVecEnv
+    cfg = make_config("solo12", task="walk", H=1, body_contacts=1)
+    env = SoloVecEnv(cfg, 4096, device="cuda:0", seed=3)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    zmin, dones = 1.0, 0
+    for t in range(60):
+        a = torch.rand(4096, 12, device="cuda", generator=g) * 2 - 1
+        obs, rew, done, _ = env.step(a)
+        st = env.sim.get_state()
+        assert torch.isfinite(st).all() and torch.isfinite(obs).all()
+        zmin = min(zmin, float(st[:, 2].min()))
+        dones += int(done.sum())
+    assert zmin > 0.0, zmin                 # the base box rests on its corners (base origin 0.025 m above them)
+    assert dones > 100
+    env.close()
+    a0 = torch.zeros(64, 12, device="cuda")
+    outs = []
+    for body in (0, 1):
+        e = SoloVecEnv(make_config("solo12", task="stand", H=1, body_contacts=body), 64, device="cuda:0", seed=3)
+        e.reset()
+        for t in range(10):
+            o, r, d, _ = e.step(a0)
+        outs.append((o.clone(), e.sim.get_state().clone()))
+        e.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

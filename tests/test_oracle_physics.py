@@ -359,3 +359,77 @@ def test_pgs_at_50_sweeps_against_a_converged_solve(robot):
     assert same < 1e-10, same
     assert exit_gap < 1.5e-3, exit_gap
     assert capped <= 4
+
+
+# ---- contacts of knees / base-box corners (SoloSimParams.body_contacts) ------------------
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_body_contact_rows_equal_dense_mass_matrix_solve(robot):
+    """The rows of knee and base-corner contacts (base-link impulse response, a second contact point on the lower
+    leg) against J M^-1 J^T from the dense CRBA mass matrix, to 1e-10; then the substep's solve against the numpy
+    PGS on that dense matrix with the sweep count the substep used (row order: limit rows, all normals, then the
+    friction pair of each point; points ordered feet, knees, lower corners, upper corners)."""
+    from tests.helpers import collapsed_states
+    rng = np.random.default_rng(17)
+    m = SoloModel.builtin(robot)
+    p = default_params()
+    p.body_contacts = 1
+    p.limit_rows_per_leg = 0          # Bullet's sequential order for the limit rows, which _reference_pgs restates
+    if robot == "solo8":
+        p.base_half_x, p.base_half_y = 0.212, 0.1046
+    e = OracleEnv(m, p)
+    nj = e.nj
+    body_rows, most, same = 0, 0, 0.0
+    for s in collapsed_states(rng, 24, robot, params=p):
+        e.set_state(s)
+        tau = rng.uniform(-1, 1, size=nj)
+        rows = e.contact_rows(tau)
+        J, U, kind, owner, target = rows["J"], rows["U"], rows["kind"], rows["owner"], rows["target"]
+        if len(J) == 0:
+            continue
+        Mb = _base_origin_mass_matrix(e, s, tau)
+        MinvJt = np.linalg.solve(Mb, J.T)
+        assert np.abs(U - MinvJt.T).max() <= 1e-10 * max(1.0, np.abs(MinvJt).max())
+        A = J @ MinvJt
+        assert np.abs(J @ U.T - A).max() <= 1e-10 * np.abs(A).max()
+        nn = int((kind == 0).sum())
+        most = max(most, nn)
+        body_rows += 3 * max(0, nn - 4)
+        e.substep(tau)
+        after = e.get_state()
+        v_sub = np.concatenate([after[10:13], after[7:10], after[13 + nj:]])
+        lam_k = _reference_pgs(A, target, kind, owner, p.friction, p.joint_limit_max_impulse, e.last_solver_iters)
+        v_ref = np.clip(rows["vstar"] + MinvJt @ lam_k, -p.max_coord_vel, p.max_coord_vel)
+        same = max(same, np.abs(v_sub - v_ref).max())
+    assert most >= 6 and body_rows >= 60, (most, body_rows)       # the sample must hold knee / corner contacts
+    assert same < 1e-9, same
+
+
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_body_contacts_hold_a_collapsed_robot(robot):
+    """Dropped flat on its belly with the legs folded up, the robot comes to rest on the lower corners of its base
+    box (base origin ~0.025 m above the ground, below the z < 0.05 termination height of baseEnv.py:169); with
+    feet-only contacts (round 1) the same robot sinks through the floor.  Switching body contacts on changes nothing
+    while only the feet are near the ground."""
+    m = SoloModel.builtin(robot)
+    nj = 8 if robot == "solo8" else 12
+    njl = nj // 4
+
+    def run(body, s0, steps):
+        p = default_params()
+        p.body_contacts = body
+        e = OracleEnv(m, p)
+        e.set_state(s0)
+        for _ in range(steps):
+            e.substep(np.zeros(nj))
+        return e.get_state()
+
+    s = np.zeros(13 + 2 * nj)
+    s[2], s[6] = 0.06, 1.0
+    for l in range(4):
+        s[13 + l * njl + njl - 2] = np.pi / 2 * (1.0 if l < 2 else -1.0) + np.pi   # upper legs pointing up
+    rest, sunk = run(1, s, 240), run(0, s, 240)
+    assert 0.015 < rest[2] < 0.035 and np.abs(rest[7:13]).max() < 0.05, rest[:13]
+    assert sunk[2] < -0.1
+    rng = np.random.default_rng(3)
+    st = stance_states(rng, 1, nj)[0]
+    assert np.array_equal(run(1, st, 40), run(0, st, 40))
