@@ -262,6 +262,124 @@ SOLO_HD int body_pgs(float* rows, unsigned lmask, unsigned pmask, const SimConst
   return it;
 }
 
+#if defined(__CUDACC__)
+/* The same sweep as body_pgs for the four lanes of an env on the GPU, without the run-time-indexed s[leg]:
+ * lane `me` keeps only the impulse sums of its own leg (s_me), so the candidate of a row is right in the lane of
+ * the row's leg alone and is handed to the siblings with one shuffle inside the group; everything else (dv0, the
+ * residual test, the record updates) is computed redundantly and identically by the four lanes.  Same arithmetic,
+ * operand for operand, as body_pgs (which the host replay runs), so the two agree bit for bit up to the
+ * compiler's FMA contraction. */
+__device__ __forceinline__ float body_resid_me(const BodyRowR& r, const float* dv0, const float* s_me) {
+  const float a = r.P[0] * dv0[0] + r.P[1] * dv0[1] + r.P[2] * dv0[2];
+  const float c = r.P[3] * dv0[3] + r.P[4] * dv0[4] + r.P[5] * dv0[5];
+  const float d = r.g[0] * s_me[0] + r.g[1] * s_me[1] + r.g[2] * s_me[2];
+  return r.b - ((a + c) + d);
+}
+__device__ __forceinline__ void body_apply_me(const BodyRowR& r, float d, bool mine, float* dv0, float* s_me) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) dv0[i] = fmaf(r.K[i], d, dv0[i]);
+  const float dm = mine ? d : 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) s_me[k] = fmaf(r.sP[k], dm, s_me[k]);
+}
+template <bool CONE>
+__device__ __forceinline__ int body_pgs_lanes(float* rows, unsigned lmask, unsigned pmask, const SimConst& sc,
+                                              unsigned gmask, unsigned gbase, int me, float* dv0, float* s_me) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) dv0[i] = 0.f;
+  s_me[0] = s_me[1] = s_me[2] = 0.f;
+  int it = 0;
+  for (; it < sc.iters;) {
+    float res = 0.f;
+    it++;
+    if (lmask) {
+      float dl[4], nl[4];
+      {
+        float nv = 0.f;
+        if ((lmask >> me) & 1u) {
+          const float* rr = rows + me * kBodyRowW;
+          BodyRowR r;
+          body_row_load(rr, r);
+          nv = fminf(fmaxf(fmaf(body_resid_me(r, dv0, s_me), r.dinv, rr[kBrLam]), 0.f), sc.lim_max_impulse);
+        }
+#pragma unroll
+        for (int l = 0; l < 4; l++) nl[l] = __shfl_sync(gmask, nv, gbase + l);
+      }
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        dl[l] = 0.f;
+        if ((lmask >> l) & 1u) {
+          const float* rr = rows + l * kBodyRowW;
+          dl[l] = nl[l] - rr[kBrLam];
+          res = fmaxf(res, fabsf(dl[l] * rr[kBrDiag]));
+        }
+      }
+      __syncwarp(gmask);
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        if ((lmask >> l) & 1u) {
+          float* rr = rows + l * kBodyRowW;
+          BodyRowR r;
+          body_row_load(rr, r);
+          rr[kBrLam] = nl[l];
+          body_apply_me(r, dl[l], l == me, dv0, s_me);
+        }
+      }
+    }
+    for (unsigned m = pmask; m; m &= m - 1) {                 /* normals of all points */
+      const int p = body_ctz(m);
+      const int leg = p & 3;
+      float* rr = rows + body_slot(p, 0) * kBodyRowW;
+      BodyRowR r;
+      body_row_load(rr, r);
+      const float lam = rr[kBrLam];
+      const float nv = __shfl_sync(gmask, fmaxf(fmaf(body_resid_me(r, dv0, s_me), r.dinv, lam), 0.f), gbase + leg);
+      const float d = nv - lam;
+      rr[kBrLam] = nv;                                        /* the shuffle above ordered the siblings' reads */
+      res = fmaxf(res, fabsf(d * r.diag));
+      body_apply_me(r, d, leg == me, dv0, s_me);
+    }
+    for (unsigned m = pmask; m; m &= m - 1) {                 /* friction pair of each point */
+      const int p = body_ctz(m);
+      const int leg = p & 3;
+      float* rn = rows + body_slot(p, 0) * kBodyRowW;
+      float* ra = rn + kBodyRowW;
+      float* rb = ra + kBodyRowW;
+      const float lim = sc.mu * rn[kBrLam];
+      BodyRowR A, B;
+      body_row_load(ra, A);
+      body_row_load(rb, B);
+      const float lamA = ra[kBrLam], lamB = rb[kBrLam];
+      if (CONE) {
+        const float sA = fmaf(body_resid_me(A, dv0, s_me), A.dinv, lamA);
+        const float sB = fmaf(body_resid_me(B, dv0, s_me), B.dinv, lamB);
+        const float n2 = fmaf(sB, sB, fmaf(sA, sA, 1e-30f));
+        const float scl = fminf(lim * solo_rsqrt(n2), 1.0f);
+        const float nA = __shfl_sync(gmask, sA * scl, gbase + leg), nB = __shfl_sync(gmask, sB * scl, gbase + leg);
+        const float dA = nA - lamA, dB = nB - lamB;
+        ra[kBrLam] = nA; rb[kBrLam] = nB;
+        res = fmaxf(res, fabsf(dA * A.diag + dB * B.diag));
+        body_apply_me(A, dA, leg == me, dv0, s_me);
+        body_apply_me(B, dB, leg == me, dv0, s_me);
+      } else {
+        const float nA = __shfl_sync(gmask, clampf(fmaf(body_resid_me(A, dv0, s_me), A.dinv, lamA), -lim, lim), gbase + leg);
+        const float dA = nA - lamA;
+        ra[kBrLam] = nA;
+        res = fmaxf(res, fabsf(dA * A.diag));
+        body_apply_me(A, dA, leg == me, dv0, s_me);
+        const float nB = __shfl_sync(gmask, clampf(fmaf(body_resid_me(B, dv0, s_me), B.dinv, lamB), -lim, lim), gbase + leg);
+        const float dB = nB - lamB;
+        rb[kBrLam] = nB;
+        res = fmaxf(res, fabsf(dB * B.diag));
+        body_apply_me(B, dB, leg == me, dv0, s_me);
+      }
+    }
+    if (res * res <= sc.res_thr) break;
+  }
+  return it;
+}
+#endif
+
 /* Joint velocity change of one leg for the joint-space impulses us[k] = s[leg][k] accumulated on it and the
  * base velocity change dv0 (impulse_leg with the impulse sums already formed). */
 template <int NJL>

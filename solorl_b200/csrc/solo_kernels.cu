@@ -538,12 +538,9 @@ __device__ __forceinline__ void contact_solve(const SimConst& sc, int leg, BaseS
       if (LIMITS) limit_setup<NJL>(sc, bw, ln, lim_env, kL, dirL, penL, lr);
       body_lane_fill<NJL>(sc, st, bw, ln, LIMITS ? &lr : nullptr, leg, foot_on != 0, bg, body_rows);
       __syncwarp(gmask);
-      float dv0[6], s[4][3];
-      const int sweeps = sc.cone ? body_pgs<true>(body_rows, lm_all, pmask, sc, gmask, dv0, s)
-                                 : body_pgs<false>(body_rows, lm_all, pmask, sc, gmask, dv0, s);
-      float us[NJL];
-#pragma unroll
-      for (int k = 0; k < NJL; k++) us[k] = body_sel(s, leg, k);
+      float dv0[6], us[3];
+      const int sweeps = sc.cone ? body_pgs_lanes<true>(body_rows, lm_all, pmask, sc, gmask, gbase, leg, dv0, us)
+                                 : body_pgs_lanes<false>(body_rows, lm_all, pmask, sc, gmask, gbase, leg, dv0, us);
       body_apply_leg<NJL>(ln, sc, us, dv0);
       float dw[3], dvl[3];
       mat3_mulv(bw.R, dv0, dw);
@@ -1222,14 +1219,19 @@ __global__ void episode_accumulate_kernel(const SoloEpisodeStats* __restrict__ s
 }
 
 /* Reverse-scan GAE (agents/ppo/storage.py:35-55), HBM-bound: 20 B per (t, env) = 4 reads + 1 write of fp32.
- * The recurrence A_t = delta_t + gamma lam m_{t+1} A_{t+1} is serial in t, but nothing it READS depends on it.
- * One thread per env walking t = T-1..0 (round 1) therefore ran at the latency of one dependent load chain
- * (4096 threads, a few loads in flight each).  Here a block owns kGaeEnvs consecutive envs and kGaeChunks
- * time chunks: thread (c, e) first loads ITS chunk's rewards / values / masks into registers -- all
- * kGaeChunks x kGaeEnvs x 3L loads of the block are independent and in flight together -- and then the
- * chunks run the recurrence one after the other, newest first, handing the running (gae, v_next) pair to
- * the next chunk through shared memory.  The arithmetic and its order are exactly those of the serial walk,
- * so results are bit-identical to the round-1 kernel and to the oracle's storage.py-order loop. */
+ * The recurrence A_t = delta_t + gamma lam m_{t+1} A_{t+1} is serial in t, but nothing it READS depends on it:
+ * delta_t = r_t + gamma V_{t+1} m_{t+1} - V_t and the factor c_t = gamma lam m_{t+1} are known up front.
+ * A block owns kGaeEnvs consecutive envs and kGaeChunks time chunks of L steps.  Thread (c, e)
+ *   1. loads ITS chunk's rewards / values / masks -- all kGaeChunks x kGaeEnvs x 3L loads of the block are
+ *      independent and in flight together -- and turns them into (c_t, delta_t) in registers;
+ *   2. the chunks then run the recurrence one after the other, newest first; on the serial path a step is ONE
+ *      fused multiply-add (the round-2 profile of the previous form, profiles/r2_gae_kernel_ncu.txt, showed 40
+ *      instructions per step there -- 64-bit address arithmetic and the store -- and 16 warps waiting for them);
+ *      the running value is handed to the next chunk through shared memory BEFORE the chunk's results are stored;
+ *   3. every thread stores its L returns (coalesced 128-byte rows), overlapping the later chunks' turns.
+ * Steps beyond T hold (c, delta) = (1, 0), i.e. leave the running value untouched, so the serial loop carries
+ * no predicate.  masks are 0/1, so folding them into c_t is exact and the arithmetic (and its rounding) is that
+ * of the serial walk below and of the oracle's storage.py-order loop. */
 constexpr int kGaeEnvs = 32;      /* one 128-byte line per [t] row and block */
 constexpr int kGaeChunks = 16;
 constexpr int kGaeMaxL = 32;      /* time steps per chunk held in registers: T <= 512 takes the chunked path */
@@ -1238,47 +1240,58 @@ __global__ void __launch_bounds__(kGaeEnvs * kGaeChunks)
 gae_chunked_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                    const float* __restrict__ masks, float* __restrict__ returns, int T, int N,
                    float gamma, float lam, int use_gae) {
-  __shared__ float carry_a[kGaeEnvs], carry_v[kGaeEnvs];
+  __shared__ float carry[kGaeEnvs];
   const int e = threadIdx.x & (kGaeEnvs - 1), c = threadIdx.x / kGaeEnvs;
   const int n = blockIdx.x * kGaeEnvs + e;
   const bool valid = n < N;
   const int nn = valid ? n : N - 1;
   /* chunk c covers t in [t0, t1), chunk kGaeChunks-1 is the newest */
   const int t0 = c * L, t1 = min(T, t0 + L);
-  float r[L], v[L], m[L];
+  const size_t stride = (size_t)N;
+  const float* pr = rewards + (size_t)t0 * stride + nn;
+  const float* pv = values + (size_t)t0 * stride + nn;
+  const float* pm = masks + (size_t)(t0 + 1) * stride + nn;
+  float cf[L], dl[L], vv[L + 1];
+#pragma unroll
+  for (int i = 0; i < L; i++) {         /* the loads: nothing below depends on another thread */
+    const bool on = t0 + i < t1;
+    dl[i] = on ? pr[(size_t)i * stride] : 0.f;
+    cf[i] = on ? pm[(size_t)i * stride] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i <= L; i++) vv[i] = (use_gae && t0 + i <= T && t0 < t1) ? pv[(size_t)i * stride] : 0.f;
+  if (c == kGaeChunks - 1) carry[e] = use_gae ? 0.f : returns[(size_t)T * stride + nn];
+  /* (c_t, delta_t) with the roundings of the reference's tensor expression (every product and sum rounded on
+   * its own: storage.py:45-47 / :52-53), no fused multiply-add */
+  const float gl = __fmul_rn(gamma, lam);
 #pragma unroll
   for (int i = 0; i < L; i++) {
-    const int t = t0 + i;
-    const bool on = t < t1;
-    const int tt = on ? t : 0;
-    r[i] = on ? rewards[(size_t)tt * N + nn] : 0.f;
-    v[i] = (on && use_gae) ? values[(size_t)tt * N + nn] : 0.f;
-    m[i] = on ? masks[(size_t)(tt + 1) * N + nn] : 0.f;
-  }
-  if (c == kGaeChunks - 1) {
-    carry_a[e] = use_gae ? 0.f : returns[(size_t)T * N + nn];
-    carry_v[e] = use_gae ? values[(size_t)T * N + nn] : 0.f;
+    const bool on = t0 + i < t1;
+    const float m = cf[i];
+    if (use_gae) {
+      dl[i] = on ? __fsub_rn(__fadd_rn(dl[i], __fmul_rn(__fmul_rn(gamma, vv[i + 1]), m)), vv[i]) : 0.f;
+      cf[i] = on ? __fmul_rn(gl, m) : 1.f;
+    } else {
+      cf[i] = on ? __fmul_rn(gamma, m) : 1.f;       /* ret = ret * gamma * m + r */
+    }
   }
   for (int turn = kGaeChunks - 1; turn >= 0; turn--) {
     __syncthreads();
-    if (turn == c && t0 < t1) {
-      float acc = carry_a[e], v_next = carry_v[e];
+    if (turn == c) {
+      float acc = carry[e];
 #pragma unroll
       for (int i = L - 1; i >= 0; i--) {
-        if (t0 + i < t1) {
-          if (use_gae) {
-            const float delta = r[i] + gamma * v_next * m[i] - v[i];
-            acc = delta + gamma * lam * m[i] * acc;
-            if (valid) returns[(size_t)(t0 + i) * N + n] = acc + v[i];
-            v_next = v[i];
-          } else {
-            acc = acc * gamma * m[i] + r[i];
-            if (valid) returns[(size_t)(t0 + i) * N + n] = acc;
-          }
-        }
+        acc = __fadd_rn(__fmul_rn(cf[i], acc), dl[i]);
+        dl[i] = acc;
       }
-      carry_a[e] = acc; carry_v[e] = v_next;
+      carry[e] = acc;
     }
+  }
+  if (valid) {
+    float* po = returns + (size_t)t0 * stride + n;
+#pragma unroll
+    for (int i = 0; i < L; i++)
+      if (t0 + i < t1) po[(size_t)i * stride] = __fadd_rn(dl[i], vv[i]);
   }
 }
 
@@ -1288,21 +1301,22 @@ __global__ void gae_kernel(const float* __restrict__ rewards, const float* __res
                            float gamma, float lam, int use_gae) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  if (use_gae) {
+  if (use_gae) {          /* same roundings as the chunked kernel (and the reference's tensor expression) */
     float gae = 0.f;
     float v_next = values[(size_t)T * N + n];
+    const float gl = __fmul_rn(gamma, lam);
     for (int t = T - 1; t >= 0; t--) {
       const float m = masks[(size_t)(t + 1) * N + n];
       const float v = values[(size_t)t * N + n];
-      const float delta = rewards[(size_t)t * N + n] + gamma * v_next * m - v;
-      gae = delta + gamma * lam * m * gae;
-      returns[(size_t)t * N + n] = gae + v;
+      const float delta = __fsub_rn(__fadd_rn(rewards[(size_t)t * N + n], __fmul_rn(__fmul_rn(gamma, v_next), m)), v);
+      gae = __fadd_rn(__fmul_rn(__fmul_rn(gl, m), gae), delta);
+      returns[(size_t)t * N + n] = __fadd_rn(gae, v);
       v_next = v;
     }
   } else {
     float ret = returns[(size_t)T * N + n];
     for (int t = T - 1; t >= 0; t--) {
-      ret = ret * gamma * masks[(size_t)(t + 1) * N + n] + rewards[(size_t)t * N + n];
+      ret = __fadd_rn(__fmul_rn(__fmul_rn(gamma, masks[(size_t)(t + 1) * N + n]), ret), rewards[(size_t)t * N + n]);
       returns[(size_t)t * N + n] = ret;
     }
   }
@@ -1374,6 +1388,14 @@ static void launch_step_variant(SoloHandle* h, const StepArgs& a, cudaStream_t s
     else step_kernel<2, MINB, WPB, false><<<blocks, kBlockThreads * WPB, 0, s>>>(a);
   }
 }
+/* shape of the throughput build: warps per block and resident blocks per SM (the register cap follows:
+ * 65536 / (32 WPB MINB)); overridable for experiments (tools/gpu_ab.py) */
+#ifndef SOLO_TP_WPB
+#define SOLO_TP_WPB 8
+#endif
+#ifndef SOLO_TP_MINB
+#define SOLO_TP_MINB 2
+#endif
 /* body_contacts: the latency shape (4 warps per block) plus the row records in dynamic shared memory */
 constexpr int kBodyWPB = 4;
 constexpr size_t kBodySmemBytes = (size_t)kBodyWPB * 8 * kBodyEnvStride * sizeof(float);
@@ -1406,7 +1428,7 @@ static void launch_step(SoloHandle* h, const StepArgs& a, cudaStream_t s) {
       if (lim) wide_step_kernel<2, true><<<blocks, kWThreads, sizeof(WideShared), s>>>(a);
       else wide_step_kernel<2, false><<<blocks, kWThreads, sizeof(WideShared), s>>>(a);
     }
-  } else if (h->variant == VARIANT_THROUGHPUT) launch_step_variant<2, 8>(h, a, s);
+  } else if (h->variant == VARIANT_THROUGHPUT) launch_step_variant<SOLO_TP_MINB, SOLO_TP_WPB>(h, a, s);
   else launch_step_variant<1, 4>(h, a, s);
   h->launches++;
 }
@@ -1852,6 +1874,8 @@ int solo_gae(const float* d_rewards, const float* d_values, const float* d_masks
     gae_chunked_kernel<8><<<blocks, threads, 0, s>>>(d_rewards, d_values, d_masks, d_returns, T, N, gamma, lam, use_gae);
   else if (T <= kGaeChunks * 16)
     gae_chunked_kernel<16><<<blocks, threads, 0, s>>>(d_rewards, d_values, d_masks, d_returns, T, N, gamma, lam, use_gae);
+  else if (T <= kGaeChunks * 25)      /* T = 400, the episode length of every shipped config */
+    gae_chunked_kernel<25><<<blocks, threads, 0, s>>>(d_rewards, d_values, d_masks, d_returns, T, N, gamma, lam, use_gae);
   else
     gae_chunked_kernel<kGaeMaxL><<<blocks, threads, 0, s>>>(d_rewards, d_values, d_masks, d_returns, T, N, gamma, lam, use_gae);
   if (cudaGetLastError() != cudaSuccess) return fail(nullptr, SOLO_E_CUDA, "gae_kernel launch failed");

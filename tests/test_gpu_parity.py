@@ -452,6 +452,26 @@ def test_gae_against_reference_golden_and_oracle():
     assert np.allclose(ret[:T].cpu().numpy(), ref[:T], rtol=2e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize("T,N", [(400, 4096), (32, 4096), (128, 100), (5, 33), (512, 64)])
+def test_gae_chunked_kernel_equals_the_serial_walk_bitwise(T, N, monkeypatch):
+    """The chunk-pipelined kernel (every T <= 512) against the one-thread-per-env serial walk: same roundings,
+    same order, so the same bits -- both modes (GAE and discounted returns), ragged N and T."""
+    from solorl_b200.sim import gae
+    g = torch.Generator(device="cuda").manual_seed(T * 7 + N)
+    r = torch.randn(T, N, device="cuda", generator=g)
+    v = torch.randn(T + 1, N, device="cuda", generator=g)
+    m = (torch.rand(T + 1, N, device="cuda", generator=g) > 0.05).float()
+    for use_gae in (True, False):
+        outs = []
+        for serial in ("0", "1"):
+            monkeypatch.setenv("SOLO_GAE_SERIAL", serial)
+            ret = torch.zeros(T + 1, N, device="cuda")
+            ret[T] = v[T]
+            gae(r, v, m, ret, 0.99, 0.95, use_gae)
+            outs.append(ret.clone())
+        assert torch.equal(outs[0], outs[1]), (T, N, use_gae)
+
+
 # ---- full BASELINE size: size-independent properties ---------------------------------------
 FULL_N = 4096
 
