@@ -378,7 +378,11 @@ __device__ __forceinline__ void pgs_sweeps4(PgsLane4& pl, const SimConst& sc, in
     for (int f = 0; f < 4; f++) {
       float nv, d, rv;
       pgs_normal_candidate(pl, nv, d, rv);
+#ifdef SOLO_EXP_NOSHFL_NORMALS   /* timing experiment only (wrong results): the normal rounds without their shuffle */
+      const float db = d;
+#else
       const float db = __shfl_sync(kFull, d, gbase + f);
+#endif
       if (leg == f) { pl.lam[0] = nv; res_own = fmaxf(res_own, fabsf(rv)); }
       pgs_apply(pl, row_of(f, 0), db);
     }

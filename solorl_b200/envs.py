@@ -277,8 +277,14 @@ class SoloBaseEnv:
         self.config = config
         self.action_space = self._vec.action_space
         self.observation_space = self._vec.observation_space
+        self._pending = None
 
     def reset(self):
+        # after a finished episode the batched step has already reset the env (masked auto-reset in the kernel,
+        # the worker's behaviour of agents/ppo/envs.py:38-40): hand that observation out instead of resetting twice
+        if self._pending is not None:
+            obs, self._pending = self._pending, None
+            return obs
         return self._vec.reset()[0].cpu().numpy().astype(np.float64)
 
     def step(self, action):
@@ -286,9 +292,12 @@ class SoloBaseEnv:
         obs, rew, done, infos = self._vec.step(a)
         d = bool(done[0].item() > 0.5)
         info = infos[0]
-        # the worker discards the terminal observation and substitutes the reset one
-        # (baseEnv.py:54, agents/ppo/envs.py:38-40); the façade returns what the worker would
-        return obs[0].cpu().numpy().astype(np.float64), float(rew[0].item()), d, info
+        o = obs[0].cpu().numpy().astype(np.float64)
+        if d:                     # baseEnv.py:54: the terminal step returns obs = None; reset() gives the next one
+            self._pending = o
+            return None, float(rew[0].item()), d, info
+        self._pending = None
+        return o, float(rew[0].item()), d, info
 
     def get_observation(self):
         return self._vec.get_observation()[0].cpu().numpy().astype(np.float64)

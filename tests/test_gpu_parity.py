@@ -568,8 +568,14 @@ def test_single_env_facade():
     o = env.reset()
     assert o.shape == (30,)
     for t in range(3):
+        assert o is not None and o.shape == (30,)
         o, r, d, info = env.step(np.zeros(8))
     assert d and info["timeout"] and info["episode_length"] == 3
+    assert o is None                                  # baseEnv.py:54: no observation on the terminal step
+    o = env.reset()                                   # the env was auto-reset by the step: its reset observation
+    assert o.shape == (30,) and np.array_equal(o, env.get_observation())
+    o2, r, d, info = env.step(np.zeros(8))
+    assert o2 is not None and not d
     env.close()
 
 
