@@ -881,9 +881,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wide_step_kernel(const __grid_co
  * torque is recomputed from the current joint state before every tick, as the external simulator's
  * SendCommand does once per control tick (baseControlEnv.py:256-270).  cmd [n][5][nj] = q_des, v_des,
  * P, D, tau_ff.  No env bookkeeping: the gait-env shell on top owns reward / termination. */
-template <int NJL>
+template <int NJL, bool BODY>
 __global__ void __launch_bounds__(kBlockThreads) actuator_kernel(const __grid_constant__ StepArgs args, int n_ticks) {
   __shared__ Smem sm;
+  extern __shared__ __align__(16) float body_smem[];   /* BODY: the row records of the warp's eight envs */
   const int tid = threadIdx.x;
   const SimConst& sc = args.sc;
   {
@@ -921,8 +922,9 @@ __global__ void __launch_bounds__(kBlockThreads) actuator_kernel(const __grid_co
     float tau[NJL];
 #pragma unroll
     for (int k = 0; k < NJL; k++) tau[k] = actuator_torque(sc, ln.q[k], ln.qd[k], qdes[k], vdes[k], P[k], D[k], tff[k]);
-    if (sc.joint_limits) group_substep<NJL, true>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet, 0, fext);
-    else group_substep<NJL, false>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet, 0, fext);
+    float* const rows = BODY ? body_smem + (size_t)el * kBodyEnvStride : nullptr;
+    if (sc.joint_limits) group_substep<NJL, true, BODY>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet, 0, fext, rows);
+    else group_substep<NJL, false, BODY>(sm.leg[leg], args.mc, sc, leg, st, ln, tau, cforce, nc_sum, sweep_feet, 0, fext, rows);
   }
   if (valid) {
     if (leg == 0) store_base(d.base, e, st, goal, potential);
@@ -1798,8 +1800,14 @@ int solo_actuator_step(SoloHandle* h, const float* d_cmd, int32_t n_ticks, void*
   cudaStream_t s = (cudaStream_t)stream;
   StepArgs a = make_step_args(h, MODE_SUBSTEP, h->n, d_cmd, nullptr, nullptr, nullptr);
   const int blocks = (h->n + 7) / 8;
-  if (h->njl == 3) actuator_kernel<3><<<blocks, kBlockThreads, 0, s>>>(a, n_ticks);
-  else actuator_kernel<2><<<blocks, kBlockThreads, 0, s>>>(a, n_ticks);
+  if (h->sc.body_contacts) {      /* 8 envs x 5 KB of row records per one-warp block: below the 48 KB default */
+    const size_t smem = (size_t)8 * kBodyEnvStride * sizeof(float);
+    if (h->njl == 3) actuator_kernel<3, true><<<blocks, kBlockThreads, smem, s>>>(a, n_ticks);
+    else actuator_kernel<2, true><<<blocks, kBlockThreads, smem, s>>>(a, n_ticks);
+  } else {
+    if (h->njl == 3) actuator_kernel<3, false><<<blocks, kBlockThreads, 0, s>>>(a, n_ticks);
+    else actuator_kernel<2, false><<<blocks, kBlockThreads, 0, s>>>(a, n_ticks);
+  }
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return SOLO_OK;

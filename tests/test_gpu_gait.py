@@ -53,6 +53,45 @@ def test_actuator_tick_matches_oracle_1e3():
     assert worst_feet < 1e-3, worst_feet
 
 
+def test_actuator_tick_with_body_contacts_matches_oracle_1e3():
+    """The actuator kernel with body_contacts on (knees and base corners on the ground, solo_body.cuh): a fallen robot
+    under the joint PD + feed-forward law, one 0.002 s tick at a time from re-injected states; 1e-3 on the samples
+    where the fp64 oracle is itself stable to a one-ulp perturbation of its input (see test_body_contact_substep_1e3)."""
+    from oracle.oracle import OracleVecEnv
+    from solorl_b200.gait import ActuatorSim
+    from tests.helpers import collapsed_states
+    rng = np.random.default_rng(5)
+    n, nj = 64, 12
+    rob = ActuatorSim(n, solo12=True, dt=0.002, device=0, seed=0, body_contacts=1)
+    assert rob.params.body_contacts == 1
+    ov, ov2 = OracleVecEnv(rob.model, rob.params, n), OracleVecEnv(rob.model, rob.params, n)
+    cur = collapsed_states(rng, n, "solo12", params=rob.params)
+    errs, sens = [], []
+    for t in range(12):
+        cmd = np.zeros((n, 5, nj), np.float32)
+        cmd[:, 0] = cur[:, 13:13 + nj] + rng.normal(size=(n, nj)) * 0.3
+        cmd[:, 2] = rng.uniform(0, 6, size=(n, nj))
+        cmd[:, 3] = rng.uniform(0, 0.3, size=(n, nj))
+        cmd[:, 4] = rng.uniform(-1, 1, size=(n, nj))
+        rob.sim.set_state(torch.from_numpy(cur.astype(np.float32)).cuda())
+        rob.sim.actuator_step(torch.from_numpy(cmd).cuda(), 1)
+        got = rob.sim.get_state().cpu().numpy().astype(np.float64)
+        c = cmd.astype(np.float64)
+        q, qd = cur[:, 13:13 + nj], cur[:, 13 + nj:]
+        tau = np.clip(c[:, 2] * (c[:, 0] - q) + c[:, 3] * (c[:, 1] - qd) + c[:, 4], -3.0, 3.0)
+        ref, _, _ = ov.substep_from(cur, tau)
+        pert, _, _ = ov2.substep_from(cur * (1 + rng.choice([-1, 1], size=cur.shape) * 6e-8), tau)
+        scale = np.maximum(1.0, np.abs(ref))
+        errs.append((np.abs(ref - got) / scale).max(axis=1))
+        sens.append((np.abs(ref - pert) / scale).max(axis=1))
+        cur = got
+    errs, sens = np.concatenate(errs), np.concatenate(sens)
+    stable = sens < 1e-4
+    assert stable.mean() > 0.9 and np.median(errs) < 1e-4
+    rate = float((errs[stable] > 1e-3).mean())
+    assert rate <= 5e-3 and errs[stable].max() < 1e-2, (rate, errs[stable].max())
+
+
 def test_feet_positions_match_oracle_1e5():
     from oracle.oracle import OracleEnv
     from tests.helpers import random_states
