@@ -419,8 +419,11 @@ __device__ __forceinline__ void pgs_sweeps4(PgsLane4& pl, const SimConst& sc, in
 __device__ long long g_narrow_trace[1024][8][8];
 __device__ int g_trace_substep;
 #define NSTAMP(i) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_narrow_trace[blockIdx.x][g_trace_sub & 7][i] = clock64(); } while (0)
+/* kernel-level stamps (slot 4 of the block's record): 0 entry, 1 after step_load, 2 before step_finish, 3 end */
+#define KSTAMP(i) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_narrow_trace[blockIdx.x][4][i] = clock64(); } while (0)
 #else
 #define NSTAMP(i) do { } while (0)
+#define KSTAMP(i) do { } while (0)
 #endif
 
 /* Second half of a substep for the four lanes of an env: contact / joint-limit rows -> Delassus rows ->
@@ -808,6 +811,7 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
   __shared__ __align__(16) StageTile stage[WPB];
   extern __shared__ __align__(16) float body_smem[];   /* BODY: the row records of the block's 8 x WPB envs */
   if (blockIdx.x * (8 * WPB) >= args.n) return;   /* padding blocks of an experiment grid (SOLO_GRID_MIN) */
+  KSTAMP(0);
   const int tid = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;      /* warp in block */
   const SimConst& sc = args.sc;
@@ -821,6 +825,7 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
   const int wslot = blockIdx.x * WPB + wib;
   EnvLane<NJL> L;
   step_load<NJL>(args, wslot, tid, stage[wib], L);
+  KSTAMP(1);
   for (int s = 0; s < nsub; s++) {                  /* frame_skip x p.stepSimulation() (solo.py:264-265) */
     if (WPB > 1) __syncthreads();   /* keep the warps of a block on the same instruction lines */
     const bool torque_on = (s == 0) || sc.torque_hold; /* SURVEY F4 */
@@ -831,7 +836,9 @@ __global__ void __launch_bounds__(kBlockThreads * WPB, MINB) step_kernel(const _
                                      L.bk.sweep_feet, s, nullptr,
                                      BODY ? body_smem + (size_t)(wib * 8 + L.el) * kBodyEnvStride : nullptr);
   }
+  KSTAMP(2);
   step_finish<NJL>(args, wslot, stage[wib], L);
+  KSTAMP(3);
 }
 
 }  // namespace solo

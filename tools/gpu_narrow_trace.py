@@ -13,7 +13,7 @@ cfg = {"model_urdf": "solo12", "mode": "headless", "episode_length": 400, "frame
 env = SoloVecEnv(cfg, n, device="cuda:0", seed=1); env.reset()
 g = torch.Generator(device="cuda").manual_seed(5)
 acts = [torch.rand(n, 12, device="cuda", generator=g) * 2 - 1 for _ in range(8)]
-L = _lib.lib(); acc = []
+L = _lib.lib(); acc = []; kacc = []
 for i in range(40):
     env.sim.step(acts[i % 8])
     if i >= 20:
@@ -22,6 +22,7 @@ for i in range(40):
         assert L.solo_debug_narrow_trace(buf.ctypes.data_as(C.c_void_p)) == 0
         nb = (n + 31) // 32
         acc.append(buf[:nb, :4, :6].copy())
+        kacc.append(buf[:nb, 4, :4].copy())
 a = np.stack(acc).astype(np.float64)       # [steps, blocks, substep, stamp]
 d = np.diff(a, axis=3)
 names = ["ABA (inward, base solve, outward)", "contact_setup", "limit select/setup + assembly + init", "PGS sweeps", "impulses + integrate"]
@@ -31,3 +32,12 @@ for k, nm in enumerate(names):
 print(f"  {'substep total':40s} " + " ".join(f"{(a[:, :, s, 5] - a[:, :, s, 0]).mean():9.0f}" for s in range(4)))
 print(f"  {'gap to the next substep':40s} " + " ".join(f"{(a[:, :, s + 1, 0] - a[:, :, s, 5]).mean():9.0f}" for s in range(3)))
 print("  whole substep loop, mean / max over blocks:", (a[:, :, 3, 5] - a[:, :, 0, 0]).mean(), (a[:, :, 3, 5] - a[:, :, 0, 0]).max(axis=1).mean())
+k = np.stack(kacc).astype(np.float64)      # [steps, blocks, stamp]: kernel entry, after step_load, before step_finish, end
+print(f"  prologue (entry -> end of step_load)      mean {(k[:, :, 1] - k[:, :, 0]).mean():9.0f}  max {(k[:, :, 1] - k[:, :, 0]).max(axis=1).mean():9.0f}")
+print(f"  substep loop                              mean {(k[:, :, 2] - k[:, :, 1]).mean():9.0f}  max {(k[:, :, 2] - k[:, :, 1]).max(axis=1).mean():9.0f}")
+print(f"  epilogue (step_finish)                    mean {(k[:, :, 3] - k[:, :, 2]).mean():9.0f}  max {(k[:, :, 3] - k[:, :, 2]).max(axis=1).mean():9.0f}")
+print(f"  whole block                               mean {(k[:, :, 3] - k[:, :, 0]).mean():9.0f}  max {(k[:, :, 3] - k[:, :, 0]).max(axis=1).mean():9.0f}")
+slow = (k[:, :, 3] - k[:, :, 0]).argmax(axis=1)
+idx = np.arange(k.shape[0])
+print(f"  slowest block of each step: prologue {(k[idx, slow, 1] - k[idx, slow, 0]).mean():.0f}, loop {(k[idx, slow, 2] - k[idx, slow, 1]).mean():.0f}, "
+      f"epilogue {(k[idx, slow, 3] - k[idx, slow, 2]).mean():.0f}")
