@@ -300,8 +300,9 @@ int solo_gae(const float* d_rewards, const float* d_values, const float* d_masks
 /* Number of kernel launches issued through this handle so far (bench evidence). */
 int64_t solo_launch_count(const SoloHandle* h);
 
-/* Which build of the step kernel this handle launches ("latency", "throughput", ...): chosen at create time from
- * the batch size, SOLO_STEP_VARIANT overrides (bench / profile evidence). */
+/* Which build of the step kernel this handle launches ("latency", "throughput", "wide", or "body" when
+ * SoloSimParams.body_contacts is set): chosen at create time from the batch size, SOLO_STEP_VARIANT overrides
+ * (bench / profile evidence). */
 const char* solo_step_variant(const SoloHandle* h);
 
 #ifdef __cplusplus

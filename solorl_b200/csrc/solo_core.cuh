@@ -784,6 +784,13 @@ template <int NR, int NC>
 struct PgsLaneT {
   float B[NR][NC];
   float g[NR], lam[NR], diag[NR];
+  /* The clamped rows (normal row 0, limit row 3) keep h = g - lambda in g[], the distance of the candidate from the
+   * current impulse, so that the impulse CHANGE is one min/max of h against pre-negated bounds -- max(h, -lambda),
+   * and min(., max - lambda) for a limit row -- instead of clamp-then-subtract: one dependent operation less per
+   * row relaxation on the sweep's chain (profiles/r2_experiments.txt item 11).  Relaxing the row
+   * itself moves h by -dlambda, which rides in the apply step as B[own row][own column] = 1. */
+  float nl0;        /* -lambda of the normal row */
+  float nl3, ul3;   /* limit row: -lambda and max_impulse - lambda */
 };
 typedef PgsLaneT<3, kRows> PgsLane;
 /* with joint-limit rows: a fourth row per lane (the leg's limit row), columns 12..15 = the four limit rows */
@@ -807,18 +814,26 @@ SOLO_HD void pgs_lane_init(const Lane<NJL>& ln, int foot, float rows[3][kRows], 
         const int c = row_of(j, n);
         const bool own_diag = (j == foot) && (n == m);
         pl.B[m][c] = (((active_mask >> j) & 1u) && !own_diag) ? rows[m][c] * invd : 0.f;
+        if (own_diag && m == 0) pl.B[m][c] = ln.active ? 1.0f : 0.f;     /* h-row: see PgsLaneT */
       }
     }
     pl.g[m] = ln.b[m] * invd;
     pl.lam[m] = 0.f;
   }
+  pl.nl0 = 0.f; pl.nl3 = 0.f; pl.ul3 = 0.f;
 }
 /* candidate for this lane's normal row: new value, impulse change, velocity residual */
 template <class PL>
 SOLO_HD void pgs_normal_candidate(const PL& pl, float& nv, float& d, float& rv) {
-  nv = fmaxf(pl.g[0], 0.f);
-  d = nv - pl.lam[0];
+  d = fmaxf(pl.g[0], pl.nl0);          /* g[0] = candidate - lambda (h-row): lambda + d = max(candidate, 0) */
+  nv = pl.lam[0] + d;
   rv = d * pl.diag[0];
+}
+/* the owner of the row takes the new impulse (the row's h moves in the apply step) */
+template <class PL>
+SOLO_HD void pgs_normal_commit(PL& pl, float nv) {
+  pl.lam[0] = nv;
+  pl.nl0 = -nv;
 }
 /* candidates for this lane's friction pair (cone) */
 template <class PL>
@@ -857,9 +872,15 @@ SOLO_HD void pgs_apply(PgsLane4& pl, int col, float d) {
 }
 /* candidate for this lane's joint-limit row: impulse in [0, max], otherwise like a normal row */
 SOLO_HD void pgs_limit_candidate(const PgsLane4& pl, float max_impulse, float& nv, float& d, float& rv) {
-  nv = fminf(fmaxf(pl.g[3], 0.f), max_impulse);
-  d = nv - pl.lam[3];
+  (void)max_impulse;
+  d = fminf(fmaxf(pl.g[3], pl.nl3), pl.ul3);   /* h-row: lambda + d = min(max(candidate, 0), max_impulse) */
+  nv = pl.lam[3] + d;
   rv = d * pl.diag[3];
+}
+SOLO_HD void pgs_limit_commit(PgsLane4& pl, float max_impulse, float nv) {
+  pl.lam[3] = nv;
+  pl.nl3 = -nv;
+  pl.ul3 = max_impulse - nv;
 }
 
 /* Four-row versions of assemble_block / pgs_lane_init: row 3 / column 12+j is the limit row of leg j.
@@ -886,7 +907,7 @@ SOLO_HD void assemble_block4(const Lane<NJL>& ln, const LimitRow<NJL>& lr, int f
 }
 template <int NJL>
 SOLO_HD void pgs_lane_init4(const Lane<NJL>& ln, const LimitRow<NJL>& lr, int foot, float rows[4][kRowsL],
-                            unsigned active_mask, unsigned limit_mask, PgsLane4& pl) {
+                            unsigned active_mask, unsigned limit_mask, float max_impulse, PgsLane4& pl) {
 #pragma unroll
   for (int m = 0; m < 4; m++) {
     const bool row_on = (m < 3) ? (ln.active != 0) : (lr.active != 0);
@@ -903,11 +924,13 @@ SOLO_HD void pgs_lane_init4(const Lane<NJL>& ln, const LimitRow<NJL>& lr, int fo
         const bool col_on = (n < 3) ? (((active_mask >> j) & 1u) != 0) : (((limit_mask >> j) & 1u) != 0);
         const bool own_diag = (j == foot) && (n == m);
         pl.B[m][c] = (col_on && !own_diag) ? rows[m][c] * invd : 0.f;
+        if (own_diag && (m == 0 || m == 3)) pl.B[m][c] = row_on ? 1.0f : 0.f;   /* h-rows: see PgsLaneT */
       }
     }
     pl.g[m] = ((m < 3) ? ln.b[m] : lr.b) * invd;
     pl.lam[m] = 0.f;
   }
+  pl.nl0 = 0.f; pl.nl3 = 0.f; pl.ul3 = max_impulse;
 }
 
 /* Wrench on the base produced by this foot's impulses, already multiplied by IA0^-1:

@@ -313,7 +313,7 @@ __device__ __forceinline__ void pgs_sweeps(PgsLane& pl, const SimConst& sc, int 
       float nv, d, rv;
       pgs_normal_candidate(pl, nv, d, rv);
       const float db = __shfl_sync(kFull, d, gbase + f);
-      if (leg == f) { pl.lam[0] = nv; res_own = fmaxf(res_own, fabsf(rv)); }
+      if (leg == f) { pgs_normal_commit(pl, nv); res_own = fmaxf(res_own, fabsf(rv)); }
       pgs_apply(pl, row_of(f, 0), db);
     }
 #pragma unroll
@@ -365,7 +365,7 @@ __device__ __forceinline__ void pgs_sweeps4(PgsLane4& pl, const SimConst& sc, in
        * sequential order; with several it is a Jacobi step among rows that couple only through the base. */
       float nv, d, rv;
       pgs_limit_candidate(pl, sc.lim_max_impulse, nv, d, rv);
-      pl.lam[3] = nv;
+      pgs_limit_commit(pl, sc.lim_max_impulse, nv);
       res_own = fmaxf(res_own, fabsf(rv));
       const float d0 = __shfl_sync(kFull, d, gbase + 0), d1 = __shfl_sync(kFull, d, gbase + 1);
       const float d2 = __shfl_sync(kFull, d, gbase + 2), d3 = __shfl_sync(kFull, d, gbase + 3);
@@ -383,7 +383,7 @@ __device__ __forceinline__ void pgs_sweeps4(PgsLane4& pl, const SimConst& sc, in
 #else
       const float db = __shfl_sync(kFull, d, gbase + f);
 #endif
-      if (leg == f) { pl.lam[0] = nv; res_own = fmaxf(res_own, fabsf(rv)); }
+      if (leg == f) { pgs_normal_commit(pl, nv); res_own = fmaxf(res_own, fabsf(rv)); }
       pgs_apply(pl, row_of(f, 0), db);
     }
 #pragma unroll
@@ -486,7 +486,7 @@ __device__ __forceinline__ void contact_solve(const SimConst& sc, int leg, BaseS
         for (int i = 0; i < 6; i++) KLj[i] = col_on ? __shfl_sync(kFull, lr.K[i], gbase + j) : 0.f;
         assemble_block4<NJL>(ln, lr, leg, j, Kj, KLj, col_on, rows);
       }
-      pgs_lane_init4<NJL>(ln, lr, leg, rows, amask, lmask, pl);
+      pgs_lane_init4<NJL>(ln, lr, leg, rows, amask, lmask, sc.lim_max_impulse, pl);
     }
     const int nc = __popc(amask);
     nc_sum += nc;
@@ -1918,6 +1918,7 @@ int solo_debug_wide_trace_helpers(long long* h_out) {
 
 const char* solo_step_variant(const SoloHandle* h) {
   if (!h) return "";
+  if (h->sc.body_contacts) return "body";    /* step_kernel<..., BODY>: the latency shape + the general contact path */
   return h->variant == VARIANT_WIDE ? "wide" : (h->variant == VARIANT_THROUGHPUT ? "throughput" : "latency");
 }
 

@@ -141,7 +141,7 @@ static void emu_substep(Emu* e, const float* tau) {
     for (int l = 0; l < 4; l++) {
       float rows[4][kRowsL];
       for (int j = 0; j < 4; j++) assemble_block4<NJL>(ln[l], lr[l], l, j, ln[j].K, lr[j].K, ((lmask >> j) & 1u) != 0, rows);
-      pgs_lane_init4<NJL>(ln[l], lr[l], l, rows, mask, lmask, pl[l]);
+      pgs_lane_init4<NJL>(ln[l], lr[l], l, rows, mask, lmask, sc.lim_max_impulse, pl[l]);
     }
     for (int it = 0; it < sc.iters; it++) {
       float res2 = 0.f;
@@ -150,7 +150,7 @@ static void emu_substep(Emu* e, const float* tau) {
         for (int f = 0; f < 4; f++) {
           float nv, rv;
           pgs_limit_candidate(pl[f], sc.lim_max_impulse, nv, dl[f], rv);
-          pl[f].lam[3] = nv;
+          pgs_limit_commit(pl[f], sc.lim_max_impulse, nv);
           res2 = fmaxf(res2, rv * rv);
         }
         for (int f = 0; f < 4; f++)
@@ -160,7 +160,7 @@ static void emu_substep(Emu* e, const float* tau) {
         if (!((mask >> f) & 1u)) continue;
         float nv, d, rv;
         pgs_normal_candidate(pl[f], nv, d, rv);
-        pl[f].lam[0] = nv;
+        pgs_normal_commit(pl[f], nv);
         for (int l = 0; l < 4; l++) pgs_apply(pl[l], row_of(f, 0), d);
         res2 = fmaxf(res2, rv * rv);
       }
@@ -201,7 +201,7 @@ static void emu_substep(Emu* e, const float* tau) {
         if (!((mask >> f) & 1u)) continue;
         float nv, d, rv;
         pgs_normal_candidate(pl[f], nv, d, rv);   /* owner lane; "shuffle" = plain read */
-        pl[f].lam[0] = nv;
+        pgs_normal_commit(pl[f], nv);
         for (int l = 0; l < 4; l++) pgs_apply(pl[l], row_of(f, 0), d);
         res2 = fmaxf(res2, rv * rv);
       }
