@@ -400,6 +400,32 @@ def time_ppo_train(cfg, n, dev, rank, world, barrier, T=32, updates=6):
                     "gradient and advantage all-reduce; whole updates, CUDA events, max over ranks"}
 
 
+def time_ppo_stand(cfg, n, dev, max_seconds=30.0, target_return=175.0):
+    """north_star: 'PPO Stand reaching the reference's return in under 5 minutes wall-clock'.  One GPU, the trainer of
+    training/train_ppo.py (solorl_b200.agents.train.train: rollouts on the CUDA vec-env, GAE kernel, PPO updates) on the
+    Stand task from random initialisation, stopped at `target_return` (mean return of the training episodes finished
+    since the last log; a standing robot collects ~0.47 per step x 400 steps = 188) or after `max_seconds`.  The
+    reference publishes no return figure, so the target is stated, not compared."""
+    import contextlib
+    from solorl_b200.agents.train import default_args, train
+    from solorl_b200.envs import SoloBaseEnv
+    args = default_args(num_agents=n, num_steps=32, mini_batch_size=4 * n, ppo_epoch=5, lr=3e-4, use_gae=True,
+                        entropy_coef=0.0, num_env_steps=int(1e10), log_interval=10, save_interval=10 ** 9,
+                        max_seconds=max_seconds, target_return=target_return, seed=2301)
+    with contextlib.redirect_stdout(sys.stderr):
+        out = train(args, dict(cfg, task="stand"), SoloBaseEnv)
+    last = out["last"]
+    hit = [h for h in out["history"] if h["episodes"] > 0 and h["episode_return"] >= target_return]
+    return {"task": "stand", "envs": n, "target_return": target_return,
+            "seconds_to_target": hit[0]["seconds"] if hit else None, "max_seconds": max_seconds,
+            "final_return": last.get("episode_return"), "final_episode_length": last.get("episode_length"),
+            "env_steps": last.get("steps"), "env_steps_per_s": last.get("fps"), "updates": out["updates"],
+            "hyper": {"num_steps": 32, "mini_batch_size": 4 * n, "ppo_epoch": 5, "lr": 3e-4, "use_gae": True,
+                      "entropy_coef": 0.0, "seed": 2301},
+            "what": "wall-clock from the first rollout (CUDA-graph capture included) to the first log line whose mean "
+                    "training-episode return reaches the target"}
+
+
 def time_saturated(cfg, dev, n, steps=60):
     """Device-resident env-steps/s of the same workload at a batch that fills the GPU (several resident waves
     of the 16-warps-per-SM throughput build), with the work counters of that run."""
@@ -735,6 +761,11 @@ def run_ours(args):
             line["reset_mode_simulate"] = time_reset_simulate(cfg, n, dev)
         except Exception as e:
             line["reset_mode_simulate"] = {"error": repr(e)[:200]}
+        if not args.no_ppo_train:
+            try:
+                line["ppo_stand"] = time_ppo_stand(cfg, n, dev)
+            except Exception as e:
+                line["ppo_stand"] = {"error": repr(e)[:300]}
         try:
             line["body_contacts"] = time_body_contacts(cfg, n, dev)
         except Exception as e:

@@ -41,6 +41,11 @@ def test_bench_line_has_every_contract_key():
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == d["unit"] and c["sample"]
     assert d["value"] > 20 * c["value"]
     assert d["policy_rollout"]["value"] > 0 and d["saturated"]["value"] > d["value"]
+    # the legs that put the rest of north_star under the driver's clock
+    assert d["ppo_train"]["value"] > 0 and d["ppo_train"]["grad_allreduce"]["pack_unpack_kernels"] == 0
+    ps = d["ppo_stand"]
+    assert ps["seconds_to_target"] is not None and ps["seconds_to_target"] < 300 and ps["final_return"] >= ps["target_return"]
+    assert d["body_contacts"]["value"] > 0 and d["gae"]["frac"] > 0.1 and d["reset_mode_simulate"]["value"] > 0
 
 
 def test_reference_arm_line():
