@@ -813,8 +813,8 @@ SOLO_HD void pgs_lane_init(const Lane<NJL>& ln, int foot, float rows[3][kRows], 
       for (int n = 0; n < 3; n++) {
         const int c = row_of(j, n);
         const bool own_diag = (j == foot) && (n == m);
-        pl.B[m][c] = (((active_mask >> j) & 1u) && !own_diag) ? rows[m][c] * invd : 0.f;
-        if (own_diag && m == 0) pl.B[m][c] = ln.active ? 1.0f : 0.f;     /* h-row: see PgsLaneT */
+        pl.B[m][c] = (((active_mask >> j) & 1u) && !own_diag) ? -(rows[m][c] * invd) : 0.f;   /* stored negated */
+        if (own_diag && m == 0) pl.B[m][c] = ln.active ? -1.0f : 0.f;    /* h-row: see PgsLaneT */
       }
     }
     pl.g[m] = ln.b[m] * invd;
@@ -861,14 +861,30 @@ SOLO_HD void pgs_pyramid_candidate(const PL& pl, float mu, int q, float& nv, flo
   d = nv - pl.lam[1 + q];
   rv = d * pl.diag[1 + q];
 }
-/* apply the impulse change d of global row `col` to this lane's rows */
+/* Apply the impulse change d of global row `col` to this lane's rows: g[m] += (-B[m][col]) d, B being stored negated.
+ * On the GPU two rows go through ONE packed FFMA2 (sm_100 fma.rn.f32x2, the scalar d broadcast by the instruction's
+ * .F32 operand form, no packing moves): the sweep is sensitive to its instruction count -- a lone warp issues a
+ * three-register FFMA every second cycle -- and the applies are 64 of its ~146 instructions
+ * (profiles/r2_experiments.txt items 12-13).  Each half is an ordinary fused multiply-add: same bits as two FFMAs. */
+SOLO_HD void pgs_fma_pair(float& g0, float& g1, float b0, float b1, float d) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long rg, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rg) : "f"(g0), "f"(g1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rd) : "f"(d));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rg) : "l"(rb), "l"(rd));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(g0), "=f"(g1) : "l"(rg));
+#else
+  g0 += b0 * d; g1 += b1 * d;
+#endif
+}
 SOLO_HD void pgs_apply(PgsLane& pl, int col, float d) {
-#pragma unroll
-  for (int m = 0; m < 3; m++) pl.g[m] -= pl.B[m][col] * d;
+  pgs_fma_pair(pl.g[0], pl.g[1], pl.B[0][col], pl.B[1][col], d);
+  pl.g[2] += pl.B[2][col] * d;
 }
 SOLO_HD void pgs_apply(PgsLane4& pl, int col, float d) {
-#pragma unroll
-  for (int m = 0; m < 4; m++) pl.g[m] -= pl.B[m][col] * d;
+  pgs_fma_pair(pl.g[0], pl.g[1], pl.B[0][col], pl.B[1][col], d);
+  pgs_fma_pair(pl.g[2], pl.g[3], pl.B[2][col], pl.B[3][col], d);
 }
 /* candidate for this lane's joint-limit row: impulse in [0, max], otherwise like a normal row */
 SOLO_HD void pgs_limit_candidate(const PgsLane4& pl, float max_impulse, float& nv, float& d, float& rv) {
@@ -923,8 +939,8 @@ SOLO_HD void pgs_lane_init4(const Lane<NJL>& ln, const LimitRow<NJL>& lr, int fo
         const int c = (n < 3) ? row_of(j, n) : limit_col(j);
         const bool col_on = (n < 3) ? (((active_mask >> j) & 1u) != 0) : (((limit_mask >> j) & 1u) != 0);
         const bool own_diag = (j == foot) && (n == m);
-        pl.B[m][c] = (col_on && !own_diag) ? rows[m][c] * invd : 0.f;
-        if (own_diag && (m == 0 || m == 3)) pl.B[m][c] = row_on ? 1.0f : 0.f;   /* h-rows: see PgsLaneT */
+        pl.B[m][c] = (col_on && !own_diag) ? -(rows[m][c] * invd) : 0.f;         /* stored negated */
+        if (own_diag && (m == 0 || m == 3)) pl.B[m][c] = row_on ? -1.0f : 0.f;  /* h-rows: see PgsLaneT */
       }
     }
     pl.g[m] = ((m < 3) ? ln.b[m] : lr.b) * invd;
