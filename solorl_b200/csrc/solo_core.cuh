@@ -100,6 +100,29 @@ SOLO_HD float dot6(const float* a, const float* b) {
   return (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + (a[3] * b[3] + a[4] * b[4] + a[5] * b[5]);
 }
 SOLO_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+/* Two dot6 against the same vector at once: on the GPU as packed FP32 (sm_100 mul / fma / add .f32x2 = SASS FMUL2 /
+ * FFMA2 / FADD2, the common operand k[i] broadcast by the instruction's scalar form), in exactly dot6's order of
+ * operations per half -- same bits, half the instructions.  The straight-line part of a substep is bound by
+ * instruction fetch (profiles/r2_icache_probe.txt), so instructions saved are cycles saved. */
+SOLO_HD void dot6_pair(const float* a, const float* b, const float* k, float& ra, float& rb) {
+#if defined(__CUDA_ARCH__)
+  /* nvcc contracts dot6's (x0 + x1 + x2) + (x3 + x4 + x5), x_i = a_i k_i, as fma(a2,k2, fma(a0,k0, a1*k1)) per
+   * half-sum: the packed form follows that order so that the bits do not change */
+  unsigned long long t, u, x, s;
+#define SOLO_PK(i) asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a[i]), "f"(b[i])); asm("mov.b64 %0, {%1, %1};" : "=l"(s) : "f"(k[i]))
+  SOLO_PK(1); asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(s));
+  SOLO_PK(0); asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(t) : "l"(x), "l"(s));
+  SOLO_PK(2); asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(t) : "l"(x), "l"(s));
+  SOLO_PK(4); asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(u) : "l"(x), "l"(s));
+  SOLO_PK(3); asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(u) : "l"(x), "l"(s));
+  SOLO_PK(5); asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(u) : "l"(x), "l"(s));
+#undef SOLO_PK
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(t) : "l"(u));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(ra), "=f"(rb) : "l"(t));
+#else
+  ra = dot6(a, k); rb = dot6(b, k);
+#endif
+}
 SOLO_HD float solo_rsqrt(float x) {   /* x >= 1e-30: one MUFU.RSQ, no denormal fix-up code */
 #if defined(__CUDA_ARCH__)
   float y;
@@ -905,17 +928,26 @@ template <int NJL>
 SOLO_HD void assemble_block4(const Lane<NJL>& ln, const LimitRow<NJL>& lr, int foot, int j, const float Kj[3][6],
                              const float* KLj, bool limit_col_on, float rows[4][kRowsL]) {
   const bool own = (j == foot);
+  /* the four rows of this lane (three contact rows, the limit row) against one column at a time, two rows per
+   * packed dot product */
 #pragma unroll
-  for (int m = 0; m < 3; m++) {
-#pragma unroll
-    for (int n = 0; n < 3; n++) rows[m][row_of(j, n)] = dot6(ln.P[m], Kj[n]) + (own ? ln.Lm[sym3_idx(m, n)] : 0.f);
+  for (int n = 0; n < 3; n++) {
+    float d0, d1, d2, d3;
+    dot6_pair(ln.P[0], ln.P[1], Kj[n], d0, d1);
+    dot6_pair(ln.P[2], lr.P, Kj[n], d2, d3);
+    rows[0][row_of(j, n)] = d0 + (own ? ln.Lm[sym3_idx(0, n)] : 0.f);
+    rows[1][row_of(j, n)] = d1 + (own ? ln.Lm[sym3_idx(1, n)] : 0.f);
+    rows[2][row_of(j, n)] = d2 + (own ? ln.Lm[sym3_idx(2, n)] : 0.f);
+    rows[3][row_of(j, n)] = d3 + (own ? lr.Lc[n] : 0.f);
   }
-#pragma unroll
-  for (int n = 0; n < 3; n++) rows[3][row_of(j, n)] = dot6(lr.P, Kj[n]) + (own ? lr.Lc[n] : 0.f);
   if (limit_col_on) {   /* uniform: some env of the warp has a limit row on leg j */
-#pragma unroll
-    for (int m = 0; m < 3; m++) rows[m][limit_col(j)] = dot6(ln.P[m], KLj) + (own ? lr.Lc[m] : 0.f);
-    rows[3][limit_col(j)] = dot6(lr.P, KLj) + (own ? lr.LL : 0.f);
+    float d0, d1, d2, d3;
+    dot6_pair(ln.P[0], ln.P[1], KLj, d0, d1);
+    dot6_pair(ln.P[2], lr.P, KLj, d2, d3);
+    rows[0][limit_col(j)] = d0 + (own ? lr.Lc[0] : 0.f);
+    rows[1][limit_col(j)] = d1 + (own ? lr.Lc[1] : 0.f);
+    rows[2][limit_col(j)] = d2 + (own ? lr.Lc[2] : 0.f);
+    rows[3][limit_col(j)] = d3 + (own ? lr.LL : 0.f);
   } else {
 #pragma unroll
     for (int m = 0; m < 4; m++) rows[m][limit_col(j)] = 0.f;
