@@ -43,7 +43,7 @@ def main():
     ns = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [4096, 16384, 65536]
     epws = sys.argv[2].split(",") if len(sys.argv) > 2 else ["latency", "throughput"]
     print(torch.cuda.get_device_name(0), flush=True)
-    for name in ("solo12", "solo8"):
+    for name in (os.environ.get("SOLO_SWEEP_ROBOTS", "solo12,solo8").split(",")):
         for n in ns:
             for epw in epws:
                 ms, nc, sw, ssum = time_cfg(name, n, epw)
