@@ -800,7 +800,8 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    # (the CPU arm never imports torch: ranks > 0 of a torchrun launch exit at once and leave the host cores to rank 0)
+    if args.impl != "reference" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         try:
             import torch.distributed as dist
             if dist.is_initialized():
