@@ -1038,6 +1038,13 @@ def test_body_contacts_result_does_not_depend_on_the_neighbours():
     for _ in range(4):
         sim.substep(cuda(tau))
     full = sim.get_state()
+    # the general path keeps its row records in shared memory, written and read by the four lanes of an env: a missing
+    # ordering between them would show up as run-to-run differences
+    for rep in range(3):
+        sim.set_state(cuda(cur))
+        for _ in range(4):
+            sim.substep(cuda(tau))
+        assert torch.equal(sim.get_state(), full), rep
     sim.close()
     for i in (0, 5, 17, 40, 63):
         one, _, _ = make_sim("solo12", 1, body_contacts=1)
