@@ -36,6 +36,18 @@ CONFIG = {"model_urdf": "solo12", "mode": "headless", "episode_length": 400, "fr
 WORKLOAD = "configs/basic12.yaml-shaped: Solo12 walk, torque control, H=1, frame_skip 4, random actions"
 
 
+def workload_config(n, world):
+    """`config` of the JSON line: the workload, IDENTICAL in both arms (`--impl ours` / `--impl reference`); what
+    differs between the arms (kernel build, host cores, how resets are produced) is reported under `run`."""
+    return {"workload": WORKLOAD, "envs_per_gpu": n, "robot": "solo12", "task": "walk", "control": "torque",
+            "num_history_stack": 1, "episode_length": 400, "frame_skip": 4, "solver_iters": 50,
+            "solver_residual_threshold": 1e-7, "joint_limits": 1, "body_contacts": 0,
+            "resets": "every auto-reset settles 5..11 zero-torque control steps (baseEnv.py:79-80): simulated by the CPU "
+                      "arm, looked up in the bit-identical reset cache by the GPU arm",
+            "l2": "GPU arm: flushed (256 MiB write) between timed steps, per-step CUDA events summed; CPU arm: not applicable",
+            "parallelism": f"env-shard x{world}"}
+
+
 def algorithmic_flops_per_env_step(nj, nc_sum, sweep_feet, frame_skip=4):
     """F_step = S (F_ABA + F_int) + sum_substeps (F_setup + F_PGS) + 400 with m = 3 nc
     rows per substep.  nc_sum = sum over the S substeps of feet in contact; sweep_feet = sum over
@@ -286,9 +298,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "env-steps/sec", "value": val, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "envs_per_step": n, "robot": "solo12", "task": "walk",
-                       "control": "torque", "num_history_stack": 1, "episode_length": 400, "solver_iters": 50,
-                       "solver_residual_threshold": 1e-7, "reset_mode": "simulate"},
+            "config": workload_config(n, int(os.environ.get("WORLD_SIZE", "1"))),
+            "run": {"envs_per_step": n, "reset_mode": "simulate", "host_threads": nthreads},
             "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": nthreads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "pybullet_direct": pyb, "reason": reason}
@@ -737,12 +748,8 @@ def run_ours(args):
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": n, "robot": "solo12", "task": "walk", "control": "torque",
-                   "num_history_stack": 1, "episode_length": 400, "solver_iters": 50,
-                   "solver_residual_threshold": 1e-7, "reset_mode": "cached", "step_kernel_build": variant,
-                   "host_cores_of_this_rank": cores,
-                   "l2": "flushed (256 MiB write) between timed steps; per-step CUDA events summed",
-                   "parallelism": f"env-shard x{world}"},
+        "config": workload_config(n, world),
+        "run": {"reset_mode": "cached", "step_kernel_build": variant, "host_cores_of_this_rank": cores},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * A * 4,
                 "d2h_bytes_per_step": n * (D + 2) * 4, "ms_per_step": e2e_s / args.steps * 1e3,

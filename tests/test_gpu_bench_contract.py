@@ -26,6 +26,10 @@ def test_bench_line_has_every_contract_key():
     assert d["n_gpus"] == 1 and d["steps"] == 30 and d["warmup"] >= 3 and d["scaling"] == "weak"
     assert d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
     assert "workload" in d["config"] and d["config"]["envs_per_gpu"] == 4096 and "model" not in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == json.loads(json.dumps(bench.workload_config(4096, 1)))    # the same dict in both arms
+    assert d["run"]["reset_mode"] == "cached" and d["run"]["step_kernel_build"] == "latency"
     assert abs(d["value"] - 4096 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
     assert d["gpu_launches"] == 30                                   # one launch of step_kernel per step
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
@@ -53,4 +57,7 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "env-steps/sec" and d["unit"] == "env-steps/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == json.loads(json.dumps(bench.workload_config(4096, 1)))
+    assert d["run"]["reset_mode"] == "simulate"
