@@ -423,6 +423,14 @@ class SoloGaitVecEnv:
         self._graph.replay()
         return tuple(t.clone() for t in self._g_out)
 
+    def reset_vel_ref(self, vel):
+        """baseControlEnv.py:236-238: impose the reference base velocity ([6] or [N, 6]); the controller reads it on
+        its next tick.  `reset_vel` is the name testing/test_ppo.py:108 calls on the vec-env."""
+        v = torch.as_tensor(np.asarray(vel, dtype=np.float32), device=self.device).reshape(-1, 6)
+        self.vel_ref = v.expand(self.nenvs, 6).clone()
+
+    reset_vel = reset_vel_ref
+
     def increment_curriculum(self, val=0.1):                                       # :321-328
         if not self.use_curriculum:
             return

@@ -263,6 +263,10 @@ def test_gait_env_pushes_and_curriculum():
     moved = (env.robot.sim.get_state()[:, :3] - calm.robot.sim.get_state()[:, :3]).abs().max().item()
     assert moved > 5e-3, moved                                   # a 8..10 N bump on a 2.5 kg robot shows within 0.96 s
     assert (env.k_tick == 6 * 80).all()
+    # reset_vel_ref (baseControlEnv.py:236-238; `reset_vel` in testing/test_ppo.py:108): the imposed reference
+    # velocity is what the next observation carries in its last six entries
+    calm.reset_vel(np.array([[0.3, 0.0, 0.0, 0.0, 0.0, 0.1]]))
+    assert torch.allclose(calm.get_observation()[:, -6:], torch.tensor([0.3, 0, 0, 0, 0, 0.1], device="cuda").expand(64, 6))
     env.close(); calm.close()
 
 
