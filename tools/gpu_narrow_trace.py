@@ -1,4 +1,6 @@
-"""Per-substep phase timing of the narrow step kernel from in-kernel cycle stamps (-DSOLO_TRACE build under tools/_ab/)."""
+"""Per-substep phase timing of the narrow step kernel from in-kernel cycle stamps (-DSOLO_TRACE build under tools/_ab/:
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -DSOLO_TRACE
+     -o tools/_ab/libsolo_trace.so solorl_b200/csrc/solo_kernels.cu)."""
 import ctypes as C, os, sys
 import numpy as np
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,6 +29,7 @@ a = np.stack(acc).astype(np.float64)       # [steps, blocks, substep, stamp]
 d = np.diff(a, axis=3)
 names = ["ABA (inward, base solve, outward)", "contact_setup", "limit select/setup + assembly + init", "PGS sweeps", "impulses + integrate"]
 print(f"{os.environ['SOLO_STEP_VARIANT']} build, {n} envs: cycles per phase, mean over blocks and steps; substeps 0..3")
+print("  (stamps 3 / 4 are only written when warp 0 of the block enters the solve: blocks whose first warp holds no contact and no\n   limit row keep stale values there, so read the per-phase rows as indicative and the kernel-level rows below as exact)")
 for k, nm in enumerate(names):
     print(f"  {nm:40s} " + " ".join(f"{d[:, :, s, k].mean():9.0f}" for s in range(4)))
 print(f"  {'substep total':40s} " + " ".join(f"{(a[:, :, s, 5] - a[:, :, s, 0]).mean():9.0f}" for s in range(4)))
